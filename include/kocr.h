@@ -1,0 +1,188 @@
+/*
+ * kocr.h - C ABI of libkocr.so, the B200 (sm_100a) implementation of karanta-ocr's page-image hot path:
+ *   page image -> smart_resize -> bicubic-AA resize -> normalise -> 14px patchify (pixel_values, image_grid_thw)
+ *   -> Qwen2-VL / Qwen2.5-VL vision tower -> merged embeddings.
+ *
+ * The reference (The-African-Research-Collective/karanta-ocr) has no FFI of its own for this path: it calls
+ * the third-party `transformers` Python API.  Each entry point below names the Python
+ * call it stands in for, as `reference call site` -> `third-party function it reaches` (HF = transformers).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns KOCR_OK (0) or a negative KOCR_ERR_* code; kocr_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - device buffers (images, pixel_values, workspace, outputs, weight sources) are allocated and owned
+ *     by the caller; the library owns only its prepacked weight copies and small planning tables.
+ *   - all device work is enqueued on the caller's stream; no call synchronises the device except
+ *     kocr_create / kocr_tower_set_weight / kocr_tower_finalize (one-time setup).
+ *   - functions in the "host planning" group touch no GPU and work on a machine without one.
+ */
+#ifndef KOCR_H_
+#define KOCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KOCR_OK 0
+#define KOCR_ERR_INVALID (-1)     /* bad argument                                   -> Python ValueError  */
+#define KOCR_ERR_ASPECT (-2)      /* smart_resize: aspect ratio > 200               -> Python ValueError  */
+#define KOCR_ERR_CUDA (-3)        /* CUDA runtime / driver failure                  -> Python RuntimeError */
+#define KOCR_ERR_UNSUPPORTED (-4) /* shape outside what the kernels were built for  -> Python RuntimeError */
+#define KOCR_ERR_STATE (-5)       /* e.g. forward before all weights were set       -> Python RuntimeError */
+
+/* resize arithmetic: which third-party fixed-point path to reproduce bit-for-bit */
+#define KOCR_RESIZE_PIL 0  /* Pillow ImagingResample 8bpc (HF "pil" backend; transformers 4.53.3 slow processor) */
+#define KOCR_RESIZE_ATEN 1 /* ATen uint8 _upsample_bicubic2d_aa (HF "torchvision" backend, transformers 5.x)     */
+
+#define KOCR_LAYOUT_CHW 0  /* uint8 [3,H,W] planar      */
+#define KOCR_LAYOUT_HWC 1  /* uint8 [H,W,3] interleaved */
+#define KOCR_LAYOUT_GRAY 2 /* uint8 [H,W]; do_convert_rgb replicates it to 3 channels */
+
+#define KOCR_DTYPE_F32 0
+#define KOCR_DTYPE_BF16 1
+#define KOCR_DTYPE_F16 2
+
+#define KOCR_ARCH_QWEN2_VL 0
+#define KOCR_ARCH_QWEN2_5_VL 1
+
+typedef struct KocrCtx KocrCtx;
+typedef struct KocrTower KocrTower;
+
+const char* kocr_last_error(void);
+const char* kocr_version(void);
+
+/* ------------------------------------------------------------------ host planning (no GPU needed) */
+
+/* HF models/qwen2_vl/image_processing_qwen2_vl.py:62-88 smart_resize (reached from
+ * karanta/training/pipeline_steps.py:289-294).  KOCR_ERR_ASPECT when max/min > 200. */
+int kocr_smart_resize(int height, int width, int factor, int64_t min_pixels, int64_t max_pixels,
+                      int* out_height, int* out_width);
+
+/* Taps per output sample of the antialiased bicubic filter: ceil(2*max(in/out,1))*2+1
+ * (Pillow precompute_coeffs / ATen _compute_index_ranges_weights). */
+int kocr_resample_ksize(int in_size, int out_size);
+
+/* Fixed-point filter bank for one axis. bounds[out_size*2] = (first tap, tap count); coeffs[out_size*ksize];
+ * *precision = right shift applied after accumulation.  mode = KOCR_RESIZE_*. */
+int kocr_resample_coeffs(int in_size, int out_size, int mode, int32_t* bounds, int32_t* coeffs, int* precision);
+
+/* lut[3*256]: the float32 a uint8 level of channel c maps to (HF image_processing_backends.py:291-331 for
+ * KOCR_RESIZE_ATEN; HF image_transforms.py rescale+normalize for KOCR_RESIZE_PIL). */
+int kocr_normalize_lut(int mode, float* lut);
+
+/* HF Qwen2VLImageProcessor.get_number_of_image_patches (image_processing_qwen2_vl.py:234-261). */
+int64_t kocr_num_patches(int height, int width, int patch, int merge, int64_t min_pixels, int64_t max_pixels);
+
+/* HF modeling_qwen2_vl.py:725-748 rot_pos_emb: pos_hw[sumN*2] = (row, col) of each patch, merge-major order. */
+int kocr_pos_ids(const int64_t* grid_thw, int n_images, int merge, int32_t* pos_hw);
+
+/* HF modeling_qwen2_vl.py:772-780: cu[sum(t)+1], int32; *n_cu receives the entry count. */
+int kocr_cu_seqlens(const int64_t* grid_thw, int n_images, int32_t* cu, int* n_cu);
+
+/* HF modeling_qwen2_5_vl.py:411-451 get_window_index (+ unique_consecutive :476).
+ * window_index[sumN/merge^2]; cu_window[<= sum windows + 1]; *n_cu_window receives the entry count. */
+int kocr_window_index(const int64_t* grid_thw, int n_images, int window_size, int merge, int patch,
+                      int32_t* window_index, int32_t* cu_window, int* n_cu_window);
+
+/* ------------------------------------------------------------------ context */
+
+/* One context per (device, caller thread).  Fails loudly (KOCR_ERR_CUDA / KOCR_ERR_UNSUPPORTED) when the
+ * device is absent or is not compute capability 10.x: there is no CPU fallback. */
+int kocr_create(int device, KocrCtx** out);
+void kocr_destroy(KocrCtx* ctx);
+
+/* ------------------------------------------------------------------ image processor (device) */
+
+typedef struct KocrImage {
+  const uint8_t* data; /* DEVICE pointer */
+  int32_t height;
+  int32_t width;
+  int32_t layout; /* KOCR_LAYOUT_* */
+  int32_t reserved;
+} KocrImage;
+
+/* Stands in for Qwen2VLImageProcessor._preprocess (HF image_processing_qwen2_vl.py:148-232), reached from
+ * karanta/training/pipeline_steps.py:289-294 and karanta/training/test_trained_model.py:82-87.
+ *   pixel_values: DEVICE [sumN, C*tps*patch*patch] in out_dtype (F32 = drop-in; BF16 = feeds the tower directly)
+ *   grid_thw_out: HOST  [n_images*3] int64 (t, h, w), input order preserved.
+ * One fused kernel per call: resize (both passes) + normalise + patch-order write. */
+int kocr_preprocess(KocrCtx* ctx, const KocrImage* images, int n_images, int64_t min_pixels, int64_t max_pixels,
+                    int resize_mode, int out_dtype, void* pixel_values, int64_t pixel_values_capacity_rows,
+                    int64_t* grid_thw_out, void* stream);
+
+/* ------------------------------------------------------------------ vision tower (device) */
+
+typedef struct KocrTowerConfig {
+  int32_t arch; /* KOCR_ARCH_* */
+  int32_t depth;
+  int32_t embed_dim;  /* Qwen2VLVisionConfig.embed_dim / Qwen2_5_VLVisionConfig.hidden_size */
+  int32_t num_heads;
+  int32_t mlp_hidden; /* embed_dim*mlp_ratio / intermediate_size */
+  int32_t out_hidden; /* Qwen2VLVisionConfig.hidden_size / Qwen2_5_VLVisionConfig.out_hidden_size */
+  int32_t patch_size;
+  int32_t temporal_patch_size;
+  int32_t in_channels;
+  int32_t spatial_merge_size;
+  int32_t window_size;
+  int32_t n_fullatt;
+  int32_t fullatt_block_indexes[8];
+} KocrTowerConfig;
+
+/* Stands in for Qwen2VisionTransformerPretrainedModel.__init__ (HF modeling_qwen2_vl.py:687-722). */
+int kocr_tower_create(KocrCtx* ctx, const KocrTowerConfig* cfg, KocrTower** out);
+void kocr_tower_destroy(KocrTower* tower);
+
+/* nn.Module.load_state_dict, one tensor at a time, under the HF key names ("blocks.3.attn.qkv.weight", ...).
+ * `data` is a DEVICE pointer to a contiguous tensor of `dtype`; it is converted to bf16 and prepacked into
+ * library-owned storage, so the caller may free it after the call returns. */
+int kocr_tower_set_weight(KocrTower* tower, const char* name, const void* data, int dtype, const int64_t* shape,
+                          int ndim);
+/* KOCR_ERR_STATE (message lists the missing keys) unless every tensor of the architecture was set. */
+int kocr_tower_finalize(KocrTower* tower);
+
+/* Bytes of caller-allocated scratch kocr_tower_forward needs for this batch. */
+int64_t kocr_tower_workspace_bytes(const KocrTower* tower, const int64_t* grid_thw, int n_images);
+
+/* Stands in for visual(pixel_values, grid_thw=...) (HF modeling_qwen2_vl.py:757-795, reached from
+ * karanta/training/ocr_training.py:86,670 via get_image_features :1118-1136; vLLM qwen2_vl.py:1376).
+ *   pixel_values: DEVICE [sumN, patch_dim], pv_dtype F32 or BF16 (cast to bf16 like PatchEmbed.forward :306-309)
+ *   grid_thw:     HOST [n_images*3] int64
+ *   out:          DEVICE [sumN/merge^2, out_hidden] bf16 (pooler_output / the 4.53.3 return value)
+ *   hidden_out:   optional DEVICE [sumN, embed_dim] bf16 (last_hidden_state), may be NULL */
+int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype, const int64_t* grid_thw,
+                       int n_images, void* out, void* hidden_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* Number of kernels the last kocr_preprocess / kocr_tower_forward on this thread launched. */
+int64_t kocr_last_launch_count(void);
+
+/* ------------------------------------------------------------------ single kernels (unit-level parity tests) */
+
+#define KOCR_EPI_NONE 0          /* C = A.B^T                                   (PatchEmbed)          */
+#define KOCR_EPI_BIAS 1          /* C = A.B^T + bias                                                   */
+#define KOCR_EPI_BIAS_QUICKGELU 2 /* x*sigmoid(1.702x)                          (VisionMlp.fc1)       */
+#define KOCR_EPI_BIAS_GELU 3     /* erf GELU                                    (PatchMerger.mlp[1])  */
+#define KOCR_EPI_BIAS_RESIDUAL 4 /* C = residual + A.B^T + bias                 (attn.proj, fc2)      */
+#define KOCR_EPI_BIAS_SWIGLU 5   /* interleaved gate/up columns -> silu(g)*u    (Qwen2_5_VLMLP)       */
+
+/* C[M,N] (bf16, row pitch ldc elements) = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major, K-contiguous. */
+int kocr_op_gemm(KocrCtx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                 const void* residual, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
+                 void* stream);
+
+/* y = LayerNorm(x)*w + b (b may be NULL -> RMSNorm when rms != 0); rows of `dim` bf16. */
+int kocr_op_norm(KocrCtx* ctx, const void* x, const float* weight, const float* bias, void* y, int64_t rows,
+                 int dim, float eps, int rms, void* stream);
+
+/* Varlen non-causal attention over packed [S, heads, 3, head_dim] q|k|v (the tower's internal QKV layout:
+ * q already rotated and pre-scaled by head_dim^-0.5*log2(e)); out [S, heads*head_dim] bf16. */
+int kocr_op_attention(KocrCtx* ctx, const void* qkv, void* out, const int32_t* cu_seqlens_host, int n_seqs,
+                      int num_heads, int head_dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOCR_H_ */

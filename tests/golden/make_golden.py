@@ -1,0 +1,217 @@
+"""Mint golden vectors from the THIRD-PARTY implementation the reference calls (transformers 5.5.0 as
+installed in the build container; the reference pins 4.53.3, /root/reference/uv.lock:2168-2169).
+
+Run once in the build container (needs /root/reference/tests/sample.jpg for config C1):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed): tests/golden/*.npz.  The reference itself holds no golden vector for this
+path, so these files are what pins the oracle under oracle/.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import preprocess_oracle as po  # noqa: E402
+from oracle import vision_oracle as vo  # noqa: E402
+
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+from PIL import Image  # noqa: E402
+from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig  # noqa: E402
+from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel  # noqa: E402
+from transformers.models.qwen2_vl.configuration_qwen2_vl import Qwen2VLVisionConfig  # noqa: E402
+from transformers.models.qwen2_vl.image_processing_pil_qwen2_vl import Qwen2VLImageProcessorPil  # noqa: E402
+from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor, smart_resize  # noqa: E402
+from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VisionTransformerPretrainedModel  # noqa: E402
+
+CKPT_MAX_PIXELS = 12845056   # Qwen2-VL / olmOCR checkpoints' preprocessor_config.json
+CLASS_MAX_PIXELS = 28 * 28 * 1280
+MIN_PIXELS = 3136
+
+
+def synth_page(h, w, seed):
+    """White page (250 +- 5) with seeded dark text-like rectangles."""
+    g = torch.Generator().manual_seed(seed)
+    img = (250 + torch.randint(-5, 6, (1, h, w), generator=g)).clamp(0, 255).repeat(3, 1, 1)
+    n = int(h * w / 2500)
+    ys = torch.randint(0, max(h - 12, 1), (n,), generator=g)
+    xs = torch.randint(0, max(w - 60, 1), (n,), generator=g)
+    ws = torch.randint(4, 60, (n,), generator=g)
+    hs = torch.randint(2, 12, (n,), generator=g)
+    cs = torch.randint(0, 90, (n, 3), generator=g)
+    for i in range(n):
+        img[:, ys[i]:ys[i] + hs[i], xs[i]:xs[i] + ws[i]] = cs[i][:, None, None]
+    return img.to(torch.uint8).numpy()
+
+
+def g1_smart_resize():
+    rng = np.random.default_rng(1)
+    cases = [(1288, 995), (1288, 910), (1024, 760), (995, 1288), (28, 28), (29, 5600), (5600, 28), (14, 14),
+             (2048, 1583), (256, 256), (1288, 420), (640, 880), (4000, 3000), (10, 1999), (27, 27), (42, 42),
+             (70, 70), (98, 126), (3584, 3584), (3585, 3583), (5000, 5000), (1, 200), (200, 1), (1, 1)]
+    for _ in range(4000):
+        cases.append((int(rng.integers(1, 2200)), int(rng.integers(1, 2200))))
+    rows = []
+    for (h, w) in cases:
+        for maxp in (CKPT_MAX_PIXELS, CLASS_MAX_PIXELS):
+            try:
+                hb, wb = smart_resize(h, w, 28, MIN_PIXELS, maxp)
+            except ValueError:
+                hb, wb = -1, -1
+            rows.append((h, w, MIN_PIXELS, maxp, hb, wb))
+    np.savez_compressed(os.path.join(HERE, "g1_smart_resize.npz"), table=np.asarray(rows, dtype=np.int64))
+    print("g1", len(rows))
+
+
+def g2_g4_pixel_values():
+    """Patch order + pixel values from both HF backends. Full arrays for small images; for page-size
+    images a strided subsample plus a float64 sum and a CRC of the bytes."""
+    import zlib
+    out = {}
+    tv = lambda maxp: Qwen2VLImageProcessor(min_pixels=MIN_PIXELS, max_pixels=maxp)
+    pil = lambda maxp: Qwen2VLImageProcessorPil(min_pixels=MIN_PIXELS, max_pixels=maxp)
+    rng = np.random.default_rng(7)
+    small = {
+        "coord_56x84": None,  # pixel value encodes (c, y, x): patch-order map (G2)
+        "noise_100x37": rng.integers(0, 256, (3, 100, 37), dtype=np.uint8),
+        "noise_61x230": rng.integers(0, 256, (3, 61, 230), dtype=np.uint8),
+        "noise_300x200": rng.integers(0, 256, (3, 300, 200), dtype=np.uint8),
+        "page_256x256": synth_page(256, 256, 11),
+    }
+    c, y, x = np.meshgrid(np.arange(3), np.arange(56), np.arange(84), indexing="ij")
+    small["coord_56x84"] = ((c * 83 + y * 3 + x) % 256).astype(np.uint8)
+    for name, img in small.items():
+        out[f"{name}.image"] = img
+        for bname, proc, arg in (("aten", tv(CKPT_MAX_PIXELS), torch.from_numpy(img)),
+                                 ("pil", pil(CKPT_MAX_PIXELS), Image.fromarray(img.transpose(1, 2, 0)))):
+            r = proc(images=[arg], return_tensors="pt")
+            out[f"{name}.{bname}.pixel_values"] = r["pixel_values"].numpy()
+            out[f"{name}.{bname}.grid"] = r["image_grid_thw"].numpy()
+    big = {
+        "letter_1288x995": (synth_page(1288, 995, 1234), CKPT_MAX_PIXELS),
+        "letter_1288x995_classmax": (synth_page(1288, 995, 1234), CLASS_MAX_PIXELS),
+        "a4_1288x910": (synth_page(1288, 910, 1235), CKPT_MAX_PIXELS),
+        "landscape_995x1288": (synth_page(995, 1288, 1236), CKPT_MAX_PIXELS),
+        "column_1288x420": (synth_page(1288, 420, 1237), CKPT_MAX_PIXELS),
+        "datagen_2048x1583": (synth_page(2048, 1583, 1238), CKPT_MAX_PIXELS),
+        "noise_1422x1056": (rng.integers(0, 256, (3, 1422, 1056), dtype=np.uint8), CKPT_MAX_PIXELS),
+    }
+    for name, (img, maxp) in big.items():
+        out[f"{name}.seed_or_shape"] = np.asarray(img.shape)
+        for bname, proc, arg in (("aten", tv(maxp), torch.from_numpy(img)),
+                                 ("pil", pil(maxp), Image.fromarray(img.transpose(1, 2, 0)))):
+            r = proc(images=[arg], return_tensors="pt")
+            pv = r["pixel_values"].numpy()
+            out[f"{name}.{bname}.grid"] = r["image_grid_thw"].numpy()
+            out[f"{name}.{bname}.sub"] = pv.reshape(-1)[::1009].copy()
+            out[f"{name}.{bname}.sum"] = np.asarray(pv.astype(np.float64).sum())
+            out[f"{name}.{bname}.crc"] = np.asarray(zlib.crc32(pv.tobytes()), dtype=np.int64)
+    # mixed batch through ONE processor call (grouping / reorder, HF :166,:184-186,:225-226)
+    mixed = [synth_page(256, 256, 21), synth_page(640, 880, 22), synth_page(256, 256, 23), synth_page(308, 196, 24)]
+    r = tv(CKPT_MAX_PIXELS)(images=[torch.from_numpy(m) for m in mixed], return_tensors="pt")
+    out["mixed.grid"] = r["image_grid_thw"].numpy()
+    out["mixed.sub"] = r["pixel_values"].numpy().reshape(-1)[::1009].copy()
+    out["mixed.crc"] = np.asarray(zlib.crc32(r["pixel_values"].numpy().tobytes()), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "g2_g4_pixel_values.npz"), **out)
+    print("g2/g4", len(out))
+
+
+def hf_qwen2(cfg: vo.TowerConfig):
+    c = Qwen2VLVisionConfig(depth=cfg.depth, embed_dim=cfg.embed_dim, hidden_size=cfg.out_hidden,
+                            mlp_ratio=cfg.mlp_hidden // cfg.embed_dim, num_heads=cfg.num_heads)
+    c._attn_implementation = "sdpa"
+    return Qwen2VisionTransformerPretrainedModel(c).eval()
+
+
+def hf_qwen25(cfg: vo.TowerConfig):
+    c = Qwen2_5_VLVisionConfig(depth=cfg.depth, hidden_size=cfg.embed_dim, intermediate_size=cfg.mlp_hidden,
+                               num_heads=cfg.num_heads, out_hidden_size=cfg.out_hidden, window_size=cfg.window_size,
+                               fullatt_block_indexes=list(cfg.fullatt_block_indexes))
+    c._attn_implementation = "sdpa"
+    return Qwen2_5_VisionTransformerPretrainedModel(c).eval()
+
+
+def g3_index_work():
+    out = {}
+    m2 = hf_qwen2(vo.TowerConfig("qwen2_vl", 1, 160, 2, 640, 256))
+    m25 = hf_qwen25(vo.TowerConfig("qwen2_5_vl", 1, 160, 2, 428, 256, fullatt_block_indexes=(0,)))
+    grids = {
+        "c1_74x54": [[1, 74, 54]], "letter_92x72": [[1, 92, 72]], "a4_92x64": [[1, 92, 64]], "thumb_20x18": [[1, 20, 18]],
+        "win_div_16x16": [[1, 16, 16]], "tiny_2x2": [[1, 2, 2]],
+        "mixed": [[1, 46, 36], [1, 92, 30], [1, 18, 18], [1, 92, 72], [1, 4, 6]], "video_t2": [[2, 8, 6], [1, 6, 10]],
+    }
+    for name, g in grids.items():
+        gt = torch.tensor(g, dtype=torch.long)
+        rot = m2.rot_pos_emb(gt)
+        out[f"{name}.grid"] = np.asarray(g, dtype=np.int64)
+        out[f"{name}.rotary_f32"] = rot.numpy()[:: max(1, rot.shape[0] // 64)]
+        cu = torch.nn.functional.pad(
+            torch.repeat_interleave(gt[:, 1] * gt[:, 2], gt[:, 0]).cumsum(0, dtype=torch.int32), (1, 0), value=0)
+        out[f"{name}.cu_seqlens"] = cu.numpy()
+        wi, cuw = m25.get_window_index(gt)
+        out[f"{name}.window_index"] = wi.numpy().astype(np.int32)
+        out[f"{name}.cu_window_seqlens"] = torch.unique_consecutive(torch.tensor(cuw, dtype=torch.int32)).numpy()
+        # pos_ids recovered from the rotary table: rot[:, 0] = row * inv_freq[0] = row, rot[:, 10|dim/4] = col
+        nf = rot.shape[1] // 2
+        out[f"{name}.pos_ids"] = np.stack([rot[:, 0].numpy().round(), rot[:, nf].numpy().round()], -1).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "g3_index_work.npz"), **out)
+    print("g3", len(out))
+
+
+@torch.no_grad()
+def g5_embeddings():
+    out = {}
+    torch.set_num_threads(os.cpu_count())
+    # C1: Qwen2-VL-2B tower on sample.jpg at longest side 1024
+    src = "/root/reference/tests/sample.jpg"
+    if os.path.exists(src):
+        im = Image.open(src).convert("RGB").resize((760, 1024), Image.BICUBIC)
+        arr = np.asarray(im).transpose(2, 0, 1).copy()
+        Image.fromarray(arr.transpose(1, 2, 0)).save(os.path.join(HERE, "sample_760x1024.png"), optimize=True)
+    else:
+        arr = np.asarray(Image.open(os.path.join(HERE, "sample_760x1024.png"))).transpose(2, 0, 1).copy()
+    cases = [
+        ("tiny_q2", vo.TowerConfig("qwen2_vl", 2, 160, 2, 640, 256), [synth_page(100, 120, 31), synth_page(60, 90, 32)], 1),
+        ("tiny_q25", vo.TowerConfig("qwen2_5_vl", 3, 160, 2, 428, 256, fullatt_block_indexes=(1,)),
+         [synth_page(300, 260, 33), synth_page(60, 90, 34)], 1),
+        ("mid_q2_d2", vo.TowerConfig("qwen2_vl", 2, 1280, 16, 5120, 1536), [synth_page(280, 252, 35)], 1),
+        ("mid_q25_d2", vo.TowerConfig("qwen2_5_vl", 2, 1280, 16, 3420, 2048, fullatt_block_indexes=(1,)),
+         [synth_page(280, 252, 36)], 1),
+        ("c1_q2_2b", vo.qwen2_vl_2b(), [arr], 8),
+    ]
+    proc = Qwen2VLImageProcessor(min_pixels=MIN_PIXELS, max_pixels=CKPT_MAX_PIXELS)
+    for name, cfg, pages, stride in cases:
+        r = proc(images=[torch.from_numpy(p) for p in pages], return_tensors="pt")
+        pv, grid = r["pixel_values"], r["image_grid_thw"]
+        sd = vo.init_weights(cfg, seed=100)
+        model = hf_qwen2(cfg) if cfg.arch == "qwen2_vl" else hf_qwen25(cfg)
+        missing = model.load_state_dict(sd, strict=True)
+        y = model(pv, grid_thw=grid)
+        emb = (y.pooler_output if hasattr(y, "pooler_output") else y).float().numpy()
+        out[f"{name}.grid"] = grid.numpy()
+        out[f"{name}.emb_rows_stride"] = np.asarray(stride)
+        out[f"{name}.emb"] = emb[::stride].copy()
+        out[f"{name}.emb_absmax"] = np.asarray(np.abs(emb).max())
+        for i, p in enumerate(pages):
+            if name != "c1_q2_2b":
+                out[f"{name}.page{i}"] = p
+        print(name, grid.tolist(), emb.shape, missing)
+    np.savez_compressed(os.path.join(HERE, "g5_embeddings.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["g1", "g3", "g24", "g5"]
+    if "g1" in which:
+        g1_smart_resize()
+    if "g3" in which:
+        g3_index_work()
+    if "g24" in which:
+        g2_g4_pixel_values()
+    if "g5" in which:
+        g5_embeddings()
