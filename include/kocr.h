@@ -22,6 +22,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define KOCR_API __attribute__((visibility("default")))
+#else
+#define KOCR_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -51,48 +57,48 @@ extern "C" {
 typedef struct KocrCtx KocrCtx;
 typedef struct KocrTower KocrTower;
 
-const char* kocr_last_error(void);
-const char* kocr_version(void);
+KOCR_API const char* kocr_last_error(void);
+KOCR_API const char* kocr_version(void);
 
 /* ------------------------------------------------------------------ host planning (no GPU needed) */
 
 /* HF models/qwen2_vl/image_processing_qwen2_vl.py:62-88 smart_resize (reached from
  * karanta/training/pipeline_steps.py:289-294).  KOCR_ERR_ASPECT when max/min > 200. */
-int kocr_smart_resize(int height, int width, int factor, int64_t min_pixels, int64_t max_pixels,
+KOCR_API int kocr_smart_resize(int height, int width, int factor, int64_t min_pixels, int64_t max_pixels,
                       int* out_height, int* out_width);
 
 /* Taps per output sample of the antialiased bicubic filter: ceil(2*max(in/out,1))*2+1
  * (Pillow precompute_coeffs / ATen _compute_index_ranges_weights). */
-int kocr_resample_ksize(int in_size, int out_size);
+KOCR_API int kocr_resample_ksize(int in_size, int out_size);
 
 /* Fixed-point filter bank for one axis. bounds[out_size*2] = (first tap, tap count); coeffs[out_size*ksize];
  * *precision = right shift applied after accumulation.  mode = KOCR_RESIZE_*. */
-int kocr_resample_coeffs(int in_size, int out_size, int mode, int32_t* bounds, int32_t* coeffs, int* precision);
+KOCR_API int kocr_resample_coeffs(int in_size, int out_size, int mode, int32_t* bounds, int32_t* coeffs, int* precision);
 
 /* lut[3*256]: the float32 a uint8 level of channel c maps to (HF image_processing_backends.py:291-331 for
  * KOCR_RESIZE_ATEN; HF image_transforms.py rescale+normalize for KOCR_RESIZE_PIL). */
-int kocr_normalize_lut(int mode, float* lut);
+KOCR_API int kocr_normalize_lut(int mode, float* lut);
 
 /* HF Qwen2VLImageProcessor.get_number_of_image_patches (image_processing_qwen2_vl.py:234-261). */
-int64_t kocr_num_patches(int height, int width, int patch, int merge, int64_t min_pixels, int64_t max_pixels);
+KOCR_API int64_t kocr_num_patches(int height, int width, int patch, int merge, int64_t min_pixels, int64_t max_pixels);
 
 /* HF modeling_qwen2_vl.py:725-748 rot_pos_emb: pos_hw[sumN*2] = (row, col) of each patch, merge-major order. */
-int kocr_pos_ids(const int64_t* grid_thw, int n_images, int merge, int32_t* pos_hw);
+KOCR_API int kocr_pos_ids(const int64_t* grid_thw, int n_images, int merge, int32_t* pos_hw);
 
 /* HF modeling_qwen2_vl.py:772-780: cu[sum(t)+1], int32; *n_cu receives the entry count. */
-int kocr_cu_seqlens(const int64_t* grid_thw, int n_images, int32_t* cu, int* n_cu);
+KOCR_API int kocr_cu_seqlens(const int64_t* grid_thw, int n_images, int32_t* cu, int* n_cu);
 
 /* HF modeling_qwen2_5_vl.py:411-451 get_window_index (+ unique_consecutive :476).
  * window_index[sumN/merge^2]; cu_window[<= sum windows + 1]; *n_cu_window receives the entry count. */
-int kocr_window_index(const int64_t* grid_thw, int n_images, int window_size, int merge, int patch,
+KOCR_API int kocr_window_index(const int64_t* grid_thw, int n_images, int window_size, int merge, int patch,
                       int32_t* window_index, int32_t* cu_window, int* n_cu_window);
 
 /* ------------------------------------------------------------------ context */
 
 /* One context per (device, caller thread).  Fails loudly (KOCR_ERR_CUDA / KOCR_ERR_UNSUPPORTED) when the
  * device is absent or is not compute capability 10.x: there is no CPU fallback. */
-int kocr_create(int device, KocrCtx** out);
-void kocr_destroy(KocrCtx* ctx);
+KOCR_API int kocr_create(int device, KocrCtx** out);
+KOCR_API void kocr_destroy(KocrCtx* ctx);
 
 /* ------------------------------------------------------------------ image processor (device) */
 
@@ -109,7 +115,7 @@ typedef struct KocrImage {
  *   pixel_values: DEVICE [sumN, C*tps*patch*patch] in out_dtype (F32 = drop-in; BF16 = feeds the tower directly)
  *   grid_thw_out: HOST  [n_images*3] int64 (t, h, w), input order preserved.
  * One fused kernel per call: resize (both passes) + normalise + patch-order write. */
-int kocr_preprocess(KocrCtx* ctx, const KocrImage* images, int n_images, int64_t min_pixels, int64_t max_pixels,
+KOCR_API int kocr_preprocess(KocrCtx* ctx, const KocrImage* images, int n_images, int64_t min_pixels, int64_t max_pixels,
                     int resize_mode, int out_dtype, void* pixel_values, int64_t pixel_values_capacity_rows,
                     int64_t* grid_thw_out, void* stream);
 
@@ -132,19 +138,19 @@ typedef struct KocrTowerConfig {
 } KocrTowerConfig;
 
 /* Stands in for Qwen2VisionTransformerPretrainedModel.__init__ (HF modeling_qwen2_vl.py:687-722). */
-int kocr_tower_create(KocrCtx* ctx, const KocrTowerConfig* cfg, KocrTower** out);
-void kocr_tower_destroy(KocrTower* tower);
+KOCR_API int kocr_tower_create(KocrCtx* ctx, const KocrTowerConfig* cfg, KocrTower** out);
+KOCR_API void kocr_tower_destroy(KocrTower* tower);
 
 /* nn.Module.load_state_dict, one tensor at a time, under the HF key names ("blocks.3.attn.qkv.weight", ...).
  * `data` is a DEVICE pointer to a contiguous tensor of `dtype`; it is converted to bf16 and prepacked into
  * library-owned storage, so the caller may free it after the call returns. */
-int kocr_tower_set_weight(KocrTower* tower, const char* name, const void* data, int dtype, const int64_t* shape,
+KOCR_API int kocr_tower_set_weight(KocrTower* tower, const char* name, const void* data, int dtype, const int64_t* shape,
                           int ndim);
 /* KOCR_ERR_STATE (message lists the missing keys) unless every tensor of the architecture was set. */
-int kocr_tower_finalize(KocrTower* tower);
+KOCR_API int kocr_tower_finalize(KocrTower* tower);
 
 /* Bytes of caller-allocated scratch kocr_tower_forward needs for this batch. */
-int64_t kocr_tower_workspace_bytes(const KocrTower* tower, const int64_t* grid_thw, int n_images);
+KOCR_API int64_t kocr_tower_workspace_bytes(const KocrTower* tower, const int64_t* grid_thw, int n_images);
 
 /* Stands in for visual(pixel_values, grid_thw=...) (HF modeling_qwen2_vl.py:757-795, reached from
  * karanta/training/ocr_training.py:86,670 via get_image_features :1118-1136; vLLM qwen2_vl.py:1376).
@@ -152,12 +158,12 @@ int64_t kocr_tower_workspace_bytes(const KocrTower* tower, const int64_t* grid_t
  *   grid_thw:     HOST [n_images*3] int64
  *   out:          DEVICE [sumN/merge^2, out_hidden] bf16 (pooler_output / the 4.53.3 return value)
  *   hidden_out:   optional DEVICE [sumN, embed_dim] bf16 (last_hidden_state), may be NULL */
-int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype, const int64_t* grid_thw,
+KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype, const int64_t* grid_thw,
                        int n_images, void* out, void* hidden_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
 /* Number of kernels the last kocr_preprocess / kocr_tower_forward on this thread launched. */
-int64_t kocr_last_launch_count(void);
+KOCR_API int64_t kocr_last_launch_count(void);
 
 /* ------------------------------------------------------------------ single kernels (unit-level parity tests) */
 
@@ -169,17 +175,17 @@ int64_t kocr_last_launch_count(void);
 #define KOCR_EPI_BIAS_SWIGLU 5   /* interleaved gate/up columns -> silu(g)*u    (Qwen2_5_VLMLP)       */
 
 /* C[M,N] (bf16, row pitch ldc elements) = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major, K-contiguous. */
-int kocr_op_gemm(KocrCtx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+KOCR_API int kocr_op_gemm(KocrCtx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
                  const void* residual, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
                  void* stream);
 
 /* y = LayerNorm(x)*w + b (b may be NULL -> RMSNorm when rms != 0); rows of `dim` bf16. */
-int kocr_op_norm(KocrCtx* ctx, const void* x, const float* weight, const float* bias, void* y, int64_t rows,
+KOCR_API int kocr_op_norm(KocrCtx* ctx, const void* x, const float* weight, const float* bias, void* y, int64_t rows,
                  int dim, float eps, int rms, void* stream);
 
 /* Varlen non-causal attention over packed [S, heads, 3, head_dim] q|k|v (the tower's internal QKV layout:
  * q already rotated and pre-scaled by head_dim^-0.5*log2(e)); out [S, heads*head_dim] bf16. */
-int kocr_op_attention(KocrCtx* ctx, const void* qkv, void* out, const int32_t* cu_seqlens_host, int n_seqs,
+KOCR_API int kocr_op_attention(KocrCtx* ctx, const void* qkv, void* out, const int32_t* cu_seqlens_host, int n_seqs,
                       int num_heads, int head_dim, void* stream);
 
 #ifdef __cplusplus

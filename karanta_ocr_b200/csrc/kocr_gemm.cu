@@ -1,0 +1,341 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA with fused epilogues (sm_100a).
+//
+//   C[M,N] = epilogue(A[M,K] . B[N,K]^T)      A, B bf16 K-major (nn.Linear layout), f32 accumulate in TMEM.
+//
+// Stands in for every nn.Linear / Conv3d the tower runs (HF models/qwen2_vl/modeling_qwen2_vl.py:304-310 PatchEmbed,
+// :401-403 qkv, :457 proj, :336-337 fc1/fc2, :324-326 merger) plus the elementwise ops HF runs after them
+// (bias, QuickGELU, GELU, residual add, RoPE :257-268), which are fused into the TMEM->register epilogue.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2-5 epilogue.
+// Tile 128 x BN x 64; UMMA 128xBNx16, cta_group::1; kStages-deep smem ring (SWIZZLE_128B); two TMEM accumulator
+// stages so the epilogue of tile i overlaps the MMAs of tile i+1. Grid = #SMs, static round-robin tile order with
+// N fastest so the CTAs running together share A row-blocks through L2.
+#include <algorithm>
+
+#include "kocr_common.cuh"
+#include "kocr_kernels.h"
+
+namespace kocr {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN > 128) ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int kAccStride = (BN > 128) ? 256 : 128;               // TMEM columns between accumulator stages
+  static constexpr int kTmemCols = 2 * kAccStride;
+};
+
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmEpilogue ep,
+            int M, int N, int K) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S::kStages * S::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full = empty_bar + S::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % S::kStages;
+          const uint32_t ph = (it / S::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          tma_load_2d(smem_a + s * S::kABytes, &tm_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d(smem_b + s * S::kBBytes, &tm_b, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        const uint32_t acc_ph = (tl >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * S::kAccStride;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % S::kStages;
+          const uint32_t ph = (it / S::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * S::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * S::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int acc = tl & 1;
+      const uint32_t acc_ph = (tl >> 1) & 1;
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * S::kAccStride + ((uint32_t)(q * 32) << 16);
+
+      if constexpr (EPI == kEpiQkvRope) {
+        // BN == 240: [q_h | k_h | v_h] of one head, 80 columns each (weights prepacked in that order).
+        const int2 pos = row_ok ? ep.pos_hw[row] : make_int2(0, 0);
+        const float2* cs_r = ep.rope_cs + (size_t)pos.x * 20;
+        const float2* cs_c = ep.rope_cs + (size_t)pos.y * 20;
+        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0;
+        const float* brow = ep.bias + n0;
+#pragma unroll 1
+        for (int sct = 0; sct < 3; ++sct) {
+          const float mul = (sct == 0) ? ep.q_scale : 1.0f;
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            uint32_t a[8], b[8];
+            tmem_ld_x8(t_row + sct * 80 + c * 8, a);
+            tmem_ld_x8(t_row + sct * 80 + 40 + c * 8, b);
+            tc_wait_ld();
+            float lo[8], hi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = c * 8 + i;
+              const float x1 = __uint_as_float(a[i]) + __ldg(brow + sct * 80 + j);
+              const float x2 = __uint_as_float(b[i]) + __ldg(brow + sct * 80 + 40 + j);
+              if (sct < 2) {
+                const float2 cs = (j < 20) ? __ldg(cs_r + j) : __ldg(cs_c + (j - 20));
+                lo[i] = (x1 * cs.x - x2 * cs.y) * mul;
+                hi[i] = (x2 * cs.x + x1 * cs.y) * mul;
+              } else {
+                lo[i] = x1;
+                hi[i] = x2;
+              }
+            }
+            if (row_ok) {
+              uint4 v0 = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]),
+                                    pack_bf16(lo[6], lo[7]));
+              uint4 v1 = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]),
+                                    pack_bf16(hi[6], hi[7]));
+              *reinterpret_cast<uint4*>(orow + sct * 80 + c * 8) = v0;
+              *reinterpret_cast<uint4*>(orow + sct * 80 + 40 + c * 8) = v1;
+            }
+          }
+        }
+      } else if constexpr (EPI == KOCR_EPI_BIAS_SWIGLU) {
+        // accumulator columns alternate gate_j, up_j; output column j = silu(gate)*up; output width N/2
+        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0 / 2;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (n0 + c * 32 >= N) break;
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
+          tc_wait_ld();
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float g = __uint_as_float(r[2 * i]) + __ldg(ep.bias + n0 + c * 32 + 2 * i);
+            const float u = __uint_as_float(r[2 * i + 1]) + __ldg(ep.bias + n0 + c * 32 + 2 * i + 1);
+            o[i] = silu(g) * u;
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+            dst[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            dst[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]),
+                                pack_bf16(o[14], o[15]));
+          }
+        }
+      } else {
+        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0;
+        const __nv_bfloat16* rrow = ep.residual + (size_t)row * ep.ld_res + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (n0 + c * 32 >= N) break;  // N is a multiple of 32
+          uint32_t r[32];
+          tmem_ld_x32(t_row + c * 32, r);
+          uint4 res[4];
+          if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) res[i] = *(reinterpret_cast<const uint4*>(rrow + c * 32) + i);
+            }
+          }
+          tc_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]);
+            if constexpr (EPI != KOCR_EPI_NONE) x += __ldg(ep.bias + n0 + c * 32 + i);
+            if constexpr (EPI == KOCR_EPI_BIAS_QUICKGELU) x = quick_gelu(x);
+            if constexpr (EPI == KOCR_EPI_BIAS_GELU) x = gelu_erf(x);
+            v[i] = x;
+          }
+          if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[2 * i] += bf16_lo(rw[i]);
+              v[2 * i + 1] += bf16_hi(rw[i]);
+            }
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+      }
+      // all of this warp's TMEM reads are complete (wait::ld above): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_one(Ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N,
+                      int K, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_kernel<BN, EPI>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    KOCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = std::min(tiles, ctx->num_sms);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep, M, N, K);
+  KOCR_LAUNCH_CHECK("gemm_kernel");
+  return KOCR_OK;
+}
+
+int launch_gemm(Ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                int epi, const GemmEpilogue& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(KOCR_ERR_INVALID, "gemm: non-positive dimension");
+  if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(KOCR_ERR_UNSUPPORTED, "gemm: dimension over 2^31");
+  if (lda % 8 || ldb % 8 || ep.ldc % 8) return fail(KOCR_ERR_UNSUPPORTED, "gemm: row pitches must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(ep.out)) & 15)
+    return fail(KOCR_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned");
+  const int bn = (epi == kEpiQkvRope) ? 240 : 256;
+  if (epi == kEpiQkvRope) {
+    if (N % 240) return fail(KOCR_ERR_UNSUPPORTED, "gemm(qkv_rope): N must be a multiple of 240");
+  } else if (epi == KOCR_EPI_BIAS_SWIGLU) {
+    if (N % 64) return fail(KOCR_ERR_UNSUPPORTED, "gemm(swiglu): N must be a multiple of 64");
+  } else if (N % 32) {
+    return fail(KOCR_ERR_UNSUPPORTED, "gemm: N must be a multiple of 32");
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tensor_map(&ta, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_tensor_map(&tb, B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  const int m = (int)M, n = (int)N, k = (int)K;
+  switch (epi) {
+    case KOCR_EPI_NONE: return launch_one<256, KOCR_EPI_NONE>(ctx, ta, tb, ep, m, n, k, stream);
+    case KOCR_EPI_BIAS: return launch_one<256, KOCR_EPI_BIAS>(ctx, ta, tb, ep, m, n, k, stream);
+    case KOCR_EPI_BIAS_QUICKGELU: return launch_one<256, KOCR_EPI_BIAS_QUICKGELU>(ctx, ta, tb, ep, m, n, k, stream);
+    case KOCR_EPI_BIAS_GELU: return launch_one<256, KOCR_EPI_BIAS_GELU>(ctx, ta, tb, ep, m, n, k, stream);
+    case KOCR_EPI_BIAS_RESIDUAL: return launch_one<256, KOCR_EPI_BIAS_RESIDUAL>(ctx, ta, tb, ep, m, n, k, stream);
+    case KOCR_EPI_BIAS_SWIGLU: return launch_one<256, KOCR_EPI_BIAS_SWIGLU>(ctx, ta, tb, ep, m, n, k, stream);
+    case kEpiQkvRope: return launch_one<240, kEpiQkvRope>(ctx, ta, tb, ep, m, n, k, stream);
+    default: return fail(KOCR_ERR_INVALID, "gemm: unknown epilogue");
+  }
+}
+
+}  // namespace kocr
+
+using namespace kocr;
+
+extern "C" int kocr_op_gemm(KocrCtx* ctx_, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                            const void* residual, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
+                            void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !A || !B || !C) return fail(KOCR_ERR_INVALID, "kocr_op_gemm: null argument");
+  if (epilogue < KOCR_EPI_NONE || epilogue > KOCR_EPI_BIAS_SWIGLU) return fail(KOCR_ERR_INVALID, "kocr_op_gemm: bad epilogue");
+  if (epilogue != KOCR_EPI_NONE && !bias) return fail(KOCR_ERR_INVALID, "kocr_op_gemm: epilogue needs a bias");
+  if (epilogue == KOCR_EPI_BIAS_RESIDUAL && !residual) return fail(KOCR_ERR_INVALID, "kocr_op_gemm: residual is null");
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.residual = static_cast<const __nv_bfloat16*>(residual);
+  ep.ld_res = ldc;
+  ep.out = static_cast<__nv_bfloat16*>(C);
+  ep.ldc = ldc;
+  reset_launch_count();
+  return launch_gemm(ctx, A, lda, B, ldb, M, N, K, epilogue, ep, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,145 @@
+"""GPU parity of the whole path through the Python surface that mirrors transformers: KarantaVisionTower against the
+fp32 CPU oracle and the golden embeddings minted from transformers. Tolerance (north_star): cosine >= 0.999 per image
+and max|d| / max|y_fp32| <= 5e-2 for the bf16 tower."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess_oracle as po
+from oracle import vision_oracle as vo
+from tests.synth import synth_page
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+CKPT_MAX = 12845056
+COS_MIN, REL_MAX = 0.999, 5e-2
+
+
+def _tower(cfg, seed=100):
+    from karanta_ocr_b200 import KarantaVisionTower
+    t = KarantaVisionTower(dict(arch=cfg.arch, depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
+                                mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden, window_size=cfg.window_size,
+                                fullatt_block_indexes=list(cfg.fullatt_block_indexes)))
+    t.load_state_dict(vo.init_weights(cfg, seed=seed))
+    return t
+
+
+def _check(out, ref, grid, what):
+    out = out.float().cpu()
+    ref = torch.as_tensor(ref).float()
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    assert torch.isfinite(out).all(), what
+    rel = ((out - ref).abs().max() / ref.abs().max()).item()
+    sizes = (np.asarray(grid).reshape(-1, 3).prod(-1) // 4).tolist()
+    coss = [torch.nn.functional.cosine_similarity(a.reshape(1, -1), b.reshape(1, -1)).item()
+            for a, b in zip(torch.split(out, sizes), torch.split(ref, sizes))]
+    assert min(coss) >= COS_MIN and rel <= REL_MAX, (what, min(coss), rel)
+    return min(coss), rel
+
+
+CASES = {
+    "tiny_q2": vo.TowerConfig("qwen2_vl", 2, 160, 2, 640, 256),
+    "tiny_q25": vo.TowerConfig("qwen2_5_vl", 3, 160, 2, 428, 256, fullatt_block_indexes=(1,)),
+    "mid_q2_d2": vo.TowerConfig("qwen2_vl", 2, 1280, 16, 5120, 1536),
+    "mid_q25_d2": vo.TowerConfig("qwen2_5_vl", 2, 1280, 16, 3420, 2048, fullatt_block_indexes=(1,)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tower_vs_transformers_golden(name):
+    from karanta_ocr_b200 import KarantaImageProcessor
+    z = np.load(os.path.join(G, "g5_embeddings.npz"))
+    cfg = CASES[name]
+    pages = [z[f"{name}.page{i}"] for i in range(8) if f"{name}.page{i}" in z.files]
+    feats = KarantaImageProcessor(min_pixels=3136, max_pixels=CKPT_MAX, device="cuda")(images=pages)
+    assert np.array_equal(feats["image_grid_thw"].cpu().numpy(), z[f"{name}.grid"])
+    tower = _tower(cfg)
+    out = tower(feats["pixel_values"], grid_thw=feats["image_grid_thw"])
+    assert out.dtype == torch.bfloat16 and out.device.type == "cuda"
+    _check(out, z[f"{name}.emb"], z[f"{name}.grid"], name)
+
+
+def test_c1_qwen2vl_2b_sample_page():
+    """Config C1: Qwen2-VL-2B tower (depth 32) on tests/sample.jpg at longest side 1024, vs the transformers fp32 golden."""
+    from PIL import Image
+    from karanta_ocr_b200 import KarantaImageProcessor
+    z = np.load(os.path.join(G, "g5_embeddings.npz"))
+    page = Image.open(os.path.join(G, "sample_760x1024.png"))
+    feats = KarantaImageProcessor(min_pixels=3136, max_pixels=CKPT_MAX, device="cuda")(images=[page])
+    assert feats["image_grid_thw"].tolist() == [[1, 74, 54]]
+    tower = _tower(vo.qwen2_vl_2b())
+    out = tower(feats["pixel_values"], grid_thw=feats["image_grid_thw"])
+    stride = int(z["c1_q2_2b.emb_rows_stride"])
+    sub = out.float().cpu()[::stride]
+    ref = torch.from_numpy(z["c1_q2_2b.emb"])
+    rel = ((sub - ref).abs().max() / float(z["c1_q2_2b.emb_absmax"])).item()
+    cos = torch.nn.functional.cosine_similarity(sub.reshape(1, -1), ref.reshape(1, -1)).item()
+    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+
+
+@pytest.mark.parametrize("arch", ["qwen2_vl", "qwen2_5_vl"])
+def test_mixed_varlen_batch_vs_oracle(arch):
+    """Config C4 flavour: mixed aspect pages in one call (cu_seqlens packing, partial tiles, tie rounding), depth 2."""
+    from karanta_ocr_b200 import PageEncoder
+    cfg = vo.TowerConfig(arch, 2, 1280, 16, 5120 if arch == "qwen2_vl" else 3420, 1536, fullatt_block_indexes=(1,))
+    pages = [synth_page(420, 640, 41), synth_page(640, 440, 42), synth_page(256, 256, 43), synth_page(644, 455, 44),
+             synth_page(130, 700, 45)]
+    tower = _tower(cfg)
+    emb, grid = PageEncoder(tower).encode(pages)
+    pv, g = po.preprocess(pages, 3136, CKPT_MAX, po.RESIZE_ATEN)
+    assert np.array_equal(grid.numpy(), g)
+    ref = vo.tower_forward(cfg, vo.init_weights(cfg, seed=100), torch.from_numpy(pv), g)
+    _check(emb, ref, g, arch)
+
+
+def test_padded_3d_pixel_values_are_flattened():
+    """DataCollator hands [B, maxN, 1176] (karanta/training/data.py:271-273); PatchEmbed flattens leading dims."""
+    cfg = CASES["tiny_q2"]
+    tower = _tower(cfg)
+    pv = torch.randn(2 * 48, 1176, generator=torch.Generator().manual_seed(1))
+    a = tower(pv, grid_thw=[[1, 8, 6], [1, 6, 8]])
+    b = tower(pv.reshape(2, 48, 1176), grid_thw=torch.tensor([[1, 8, 6], [1, 6, 8]]))
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        tower(pv[:50], grid_thw=[[1, 8, 6], [1, 6, 8]])
+
+
+def test_missing_weights_fail_loudly():
+    from karanta_ocr_b200 import KarantaVisionTower
+    cfg = CASES["tiny_q2"]
+    t = KarantaVisionTower(dict(arch="qwen2_vl", depth=2, embed_dim=160, num_heads=2, mlp_hidden=640, out_hidden=256))
+    sd = vo.init_weights(cfg, seed=1)
+    sd.pop("blocks.1.mlp.fc2.bias")
+    with pytest.raises(RuntimeError, match="blocks.1.mlp.fc2.bias"):
+        t.load_state_dict(sd)
+    with pytest.raises(RuntimeError):
+        t(torch.zeros(16, 1176), grid_thw=[[1, 4, 4]])
+
+
+def test_full_letter_page_depth4_vs_oracle():
+    """One C2 page (1288x995 -> 92x72 grid, 6624 patches, 26 query blocks x 52 key tiles per head), 7B widths, depth 4."""
+    from karanta_ocr_b200 import PageEncoder
+    cfg = vo.qwen2_vl_7b(depth=4)
+    page = synth_page(1288, 995, 1234)
+    emb, grid = PageEncoder(_tower(cfg)).encode([page])
+    assert grid.tolist() == [[1, 92, 72]] and emb.shape == (1656, 3584)
+    pv, g = po.preprocess([page], 3136, CKPT_MAX, po.RESIZE_ATEN)
+    torch.set_num_threads(os.cpu_count())
+    ref = vo.tower_forward(cfg, vo.init_weights(cfg, seed=100), torch.from_numpy(pv), g)
+    _check(emb, ref, g, "letter_d4")
+
+
+def test_batch_equals_single_pages():
+    """Pages are independent: a page's embeddings do not depend on what else is in the batch (bit-exact)."""
+    from karanta_ocr_b200 import PageEncoder
+    cfg = vo.qwen2_vl_7b(depth=2)
+    enc = PageEncoder(_tower(cfg))
+    pages = [synth_page(644, 504, 50 + i) for i in range(3)] + [synth_page(392, 700, 60)]
+    emb, grid = enc.encode(pages)
+    sizes = (grid.numpy().prod(-1) // 4).tolist()
+    parts = torch.split(emb, sizes)
+    for i in (0, 3):
+        one, _ = enc.encode([pages[i]])
+        assert torch.equal(one, parts[i])
