@@ -165,6 +165,13 @@ KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int 
 /* Number of kernels the last kocr_preprocess / kocr_tower_forward on this thread launched. */
 KOCR_API int64_t kocr_last_launch_count(void);
 
+/* Per-kernel-class device timing (CUDA events on the launching stream) for bench.py's roofline numbers.
+ * kocr_profile_begin starts recording around every launch made through this ctx; kocr_profile_end waits for the
+ * recorded events, fills ms_per_class / launches_per_class (max_classes entries) and returns the class count. */
+KOCR_API int kocr_profile_begin(KocrCtx* ctx);
+KOCR_API int kocr_profile_end(KocrCtx* ctx, int max_classes, double* ms_per_class, int64_t* launches_per_class);
+KOCR_API const char* kocr_profile_class_name(int cls);
+
 /* ------------------------------------------------------------------ single kernels (unit-level parity tests) */
 
 #define KOCR_EPI_NONE 0          /* C = A.B^T                                   (PatchEmbed)          */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "kocr_tower_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "kocr_last_launch_count": (C.c_int64, []),
+    "kocr_profile_begin": (C.c_int, [C.c_void_p]),
+    "kocr_profile_end": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kocr_profile_class_name": (C.c_char_p, [C.c_int]),
     "kocr_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "kocr_op_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,

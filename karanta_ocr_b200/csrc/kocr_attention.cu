@@ -166,7 +166,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    setmaxnreg_inc<208>();
+    setmaxnreg_inc<200>();  // 128*96 + 256*200 <= 384*168 (the launch allocation): inc can never starve
     const int t = (warp - 4) >> 2;   // query tile
     const int qtr = warp & 3;        // TMEM lane quarter
     const int r = qtr * 32 + lane;   // row within the tile

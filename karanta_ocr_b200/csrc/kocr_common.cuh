@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/kocr.h"
 
@@ -65,6 +66,33 @@ struct Ctx {
   // begin/commit variant: fill the pinned slot in place
   int stage_begin(size_t bytes, void** h_out, int* slot);
   int stage_commit(int slot, size_t bytes, cudaStream_t stream, void** d_out);
+  // optional per-kernel-class timing with CUDA events on the launching stream (kocr_profile_begin / _end)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int cls; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_event();
+};
+
+enum ProfClass { kProfPreprocess = 0, kProfPatchEmbed, kProfNorm, kProfQkvRope, kProfAttention, kProfProj, kProfFc1, kProfFc2,
+                 kProfMerger, kProfOther, kProfClasses };
+
+// Records an event pair around the launches issued in its scope when profiling is on; free otherwise.
+struct ProfScope {
+  Ctx* ctx;
+  cudaStream_t st;
+  size_t idx = 0;
+  bool on;
+  ProfScope(Ctx* c, int cls, cudaStream_t s) : ctx(c), st(s), on(c && c->prof_on) {
+    if (!on) return;
+    Ctx::ProfRec r{ctx->prof_event(), ctx->prof_event(), cls};
+    cudaEventRecord(r.a, st);
+    idx = ctx->prof_recs.size();
+    ctx->prof_recs.push_back(r);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(ctx->prof_recs[idx].b, st);
+  }
 };
 
 // ----------------------------------------------------------------------------------------------- device side

@@ -285,11 +285,62 @@ int Ctx::stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out)
   return stage_commit(s, bytes, stream, d_out);
 }
 
+cudaEvent_t Ctx::prof_event() {
+  if (!prof_pool.empty()) {
+    cudaEvent_t e = prof_pool.back();
+    prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static const char* kProfNames[kProfClasses] = {"preprocess", "gemm_patch_embed", "norm", "gemm_qkv_rope", "attention",
+                                               "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_merger", "other"};
+
 }  // namespace kocr
 
 using namespace kocr;
 
 extern "C" {
+
+int kocr_profile_begin(KocrCtx* ctx_) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx_);
+  if (!c) return fail(KOCR_ERR_INVALID, "kocr_profile_begin: null ctx");
+  for (auto& r : c->prof_recs) {
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  c->prof_on = true;
+  return KOCR_OK;
+}
+
+int kocr_profile_end(KocrCtx* ctx_, int max_classes, double* ms_per_class, int64_t* launches_per_class) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx_);
+  if (!c || !ms_per_class || !launches_per_class) return fail(KOCR_ERR_INVALID, "kocr_profile_end: null argument");
+  c->prof_on = false;
+  for (int i = 0; i < max_classes; ++i) {
+    ms_per_class[i] = 0;
+    launches_per_class[i] = 0;
+  }
+  for (auto& r : c->prof_recs) {
+    KOCR_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float ms = 0;
+    KOCR_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.cls < max_classes) {
+      ms_per_class[r.cls] += ms;
+      launches_per_class[r.cls] += 1;
+    }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  return kProfClasses;
+}
+
+const char* kocr_profile_class_name(int cls) { return (cls >= 0 && cls < kProfClasses) ? kProfNames[cls] : ""; }
 
 const char* kocr_last_error(void) { return g_err.c_str(); }
 const char* kocr_version(void) { return "kocr 0.1 (sm_100a)"; }
@@ -377,6 +428,8 @@ void kocr_destroy(KocrCtx* ctx) {
   }
   for (int mode = 0; mode < 2; ++mode)
     if (c->d_lut[mode]) cudaFree(c->d_lut[mode]);
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   delete c;
 }
 

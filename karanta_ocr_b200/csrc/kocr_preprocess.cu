@@ -156,7 +156,6 @@ static int get_table(int in_size, int out_size, int mode, const AxisTable** out)
   auto& cache = table_cache();
   auto it = cache.find(key);
   if (it == cache.end()) {
-    if (cache.size() > 256) cache.clear();
     AxisTable t;
     t.ksize = resample_ksize(in_size, out_size);
     t.bounds.resize((size_t)out_size * 2);
@@ -193,6 +192,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     return fail(KOCR_ERR_INVALID, "kocr_preprocess: pixel_values must be 8-byte aligned");
 
   // ---- plan on the host: sizes, filter banks (deduplicated), tiles
+  if (table_cache().size() > 256) table_cache().clear();  // bound the per-thread cache (pointers below stay valid)
   std::vector<PageJob> jobs(n_images);
   struct Need { const AxisTable* t; size_t off_b, off_c; };
   std::map<const AxisTable*, Need> needs;
@@ -278,6 +278,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   const int smem = max_mid + max_res;
   const int grid = std::min(tiles, ctx->num_sms * 8);
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
+  ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
     KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],

@@ -384,6 +384,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   // ---- patch embed (HF :304-310; Conv3d with kernel == stride is a GEMM over the flattened patch)
   const void* pv = pixel_values;
   if (pv_dtype == KOCR_DTYPE_F32) {
+    ProfScope ps(ctx, kProfOther, st);
     if ((rc = launch_cast_f32_bf16(static_cast<const float*>(pixel_values), ws + wl.pv, (int64_t)S * t->PD, st))) return rc;
     pv = ws + wl.pv;
   }
@@ -391,8 +392,12 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   __nv_bfloat16* x_embed = t->q25 ? x2 : x;
   ep.out = x_embed;
   ep.ldc = D;
-  if ((rc = launch_gemm(ctx, pv, t->PD, t->w_patch, t->PD, S, D, t->PD, KOCR_EPI_NONE, ep, st))) return rc;
+  {
+    ProfScope ps(ctx, kProfPatchEmbed, st);
+    if ((rc = launch_gemm(ctx, pv, t->PD, t->w_patch, t->PD, S, D, t->PD, KOCR_EPI_NONE, ep, st))) return rc;
+  }
   if (t->q25) {  // window-major permutation of 4-patch groups (HF qwen2_5 :478-481)
+    ProfScope ps(ctx, kProfOther, st);
     if ((rc = launch_gather_groups(x2, x, d_wi, S / 4, 4, D, false, st))) return rc;
   }
 
@@ -405,29 +410,51 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
       for (int k = 0; k < t->cfg.n_fullatt; ++k) full |= t->cfg.fullatt_block_indexes[k] == i;
     }
     // norm1 -> qkv (+bias, RoPE, q scale) -> attention -> proj (+bias, +residual)
-    if ((rc = launch_norm(x, D, b.n1w, t->q25 ? nullptr : b.n1b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
+    {
+      ProfScope ps(ctx, kProfNorm, st);
+      if ((rc = launch_norm(x, D, b.n1w, t->q25 ? nullptr : b.n1b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
+    }
     GemmEpilogue e1{};
     e1.bias = b.b_qkv; e1.out = qkv; e1.ldc = 3 * D; e1.pos_hw = d_pos; e1.rope_cs = t->rope_cs; e1.q_scale = q_scale;
-    if ((rc = launch_gemm(ctx, xn, D, b.w_qkv, D, S, 3 * D, D, kEpiQkvRope, e1, st))) return rc;
-    if (full) rc = launch_attention(ctx, qkv, attn, d_wf, (int)work_full.size(), H, S, st);
-    else rc = launch_attention(ctx, qkv, attn, d_ww, (int)work_win.size(), H, S, st);
-    if (rc) return rc;
+    {
+      ProfScope ps(ctx, kProfQkvRope, st);
+      if ((rc = launch_gemm(ctx, xn, D, b.w_qkv, D, S, 3 * D, D, kEpiQkvRope, e1, st))) return rc;
+    }
+    {
+      ProfScope ps(ctx, kProfAttention, st);
+      if (full) rc = launch_attention(ctx, qkv, attn, d_wf, (int)work_full.size(), H, S, st);
+      else rc = launch_attention(ctx, qkv, attn, d_ww, (int)work_win.size(), H, S, st);
+      if (rc) return rc;
+    }
     GemmEpilogue e2{};
     e2.bias = b.b_proj; e2.residual = x; e2.ld_res = D; e2.out = x; e2.ldc = D;
-    if ((rc = launch_gemm(ctx, attn, D, b.w_proj, D, S, D, D, KOCR_EPI_BIAS_RESIDUAL, e2, st))) return rc;
+    {
+      ProfScope ps(ctx, kProfProj, st);
+      if ((rc = launch_gemm(ctx, attn, D, b.w_proj, D, S, D, D, KOCR_EPI_BIAS_RESIDUAL, e2, st))) return rc;
+    }
     // norm2 -> mlp
-    if ((rc = launch_norm(x, D, b.n2w, t->q25 ? nullptr : b.n2b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
+    {
+      ProfScope ps(ctx, kProfNorm, st);
+      if ((rc = launch_norm(x, D, b.n2w, t->q25 ? nullptr : b.n2b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
+    }
     GemmEpilogue e3{};
     e3.bias = b.b_fc1; e3.out = hbuf; e3.ldc = Fp;
-    if (!t->q25) rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, Fp, D, KOCR_EPI_BIAS_QUICKGELU, e3, st);
-    else rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, 2 * Fp, D, KOCR_EPI_BIAS_SWIGLU, e3, st);
-    if (rc) return rc;
+    {
+      ProfScope ps(ctx, kProfFc1, st);
+      if (!t->q25) rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, Fp, D, KOCR_EPI_BIAS_QUICKGELU, e3, st);
+      else rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, 2 * Fp, D, KOCR_EPI_BIAS_SWIGLU, e3, st);
+      if (rc) return rc;
+    }
     GemmEpilogue e4{};
     e4.bias = b.b_fc2; e4.residual = x; e4.ld_res = D; e4.out = x; e4.ldc = D;
-    if ((rc = launch_gemm(ctx, hbuf, Fp, b.w_fc2, Fp, S, D, Fp, KOCR_EPI_BIAS_RESIDUAL, e4, st))) return rc;
+    {
+      ProfScope ps(ctx, kProfFc2, st);
+      if ((rc = launch_gemm(ctx, hbuf, Fp, b.w_fc2, Fp, S, D, Fp, KOCR_EPI_BIAS_RESIDUAL, e4, st))) return rc;
+    }
   }
 
   // ---- merger (HF :313-326): LN -> view(-1, 4D) (free: 4 consecutive tokens are one merge cell) -> GEMM+GELU -> GEMM
+  ProfScope ps_merger(ctx, kProfMerger, st);
   if ((rc = launch_norm(x, D, t->ln_w, t->q25 ? nullptr : t->ln_b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
   GemmEpilogue e5{};
   e5.bias = t->b_m0; e5.out = qkv; e5.ldc = 4 * D;
