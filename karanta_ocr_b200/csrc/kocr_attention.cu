@@ -40,6 +40,30 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                  const AttnWork* __restrict__ work, int num_heads) {
@@ -189,23 +213,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         for (int c = 0; c < 128; ++c)
           if (c >= valid) sr[c] = 0xff800000u;  // -inf
       }
-      float mx = __uint_as_float(sr[0]);
+      // row max: 4 independent FMNMX3 chains (a single chain of 127 dependent max ops would cost ~500 cycles)
+      float mxa[4];
 #pragma unroll
-      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      for (int g = 0; g < 4; ++g) {
+        mxa[g] = max3(__uint_as_float(sr[32 * g]), __uint_as_float(sr[32 * g + 1]), __uint_as_float(sr[32 * g + 2]));
+#pragma unroll
+        for (int c = 3; c < 31; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[32 * g + c]), __uint_as_float(sr[32 * g + c + 1]));
+        mxa[g] = fmaxf(mxa[g], __uint_as_float(sr[32 * g + 31]));
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       float alpha = 1.0f;
       const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first tile (m_ref = -inf)
       if (grow) {
         alpha = ex2(m_ref - mx);  // 0 on the first tile
         m_ref = mx;
       }
-      float sum = 0.f;
+      // p = 2^(s - m): packed f32x2 subtract and 4 independent packed row-sum accumulators
+      const uint64_t neg_m2 = pack_f32x2(-m_ref, -m_ref);
+      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const float p0 = ex2(__uint_as_float(sr[2 * c]) - m_ref);
-        const float p1 = ex2(__uint_as_float(sr[2 * c + 1]) - m_ref);
-        sum += p0 + p1;
+        float x0, x1;
+        unpack_f32x2(add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2), x0, x1);
+        const float p0 = ex2(x0), p1 = ex2(x1);
+        acc2[c & 3] = add_f32x2(acc2[c & 3], pack_f32x2(p0, p1));
         pk[c] = pack_bf16(p0, p1);
+      }
+      float sum;
+      {
+        float a0, a1, b0, b1;
+        unpack_f32x2(add_f32x2(acc2[0], acc2[1]), a0, a1);
+        unpack_f32x2(add_f32x2(acc2[2], acc2[3]), b0, b1);
+        sum = (a0 + a1) + (b0 + b1);
       }
       l = l * alpha + sum;
       tmem_st_x16(t_s, pk);

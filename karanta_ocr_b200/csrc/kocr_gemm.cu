@@ -6,7 +6,7 @@
 // :401-403 qkv, :457 proj, :336-337 fc1/fc2, :324-326 merger) plus the elementwise ops HF runs after them
 // (bias, QuickGELU, GELU, residual add, RoPE :257-268), which are fused into the TMEM->register epilogue.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2-5 epilogue.
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2-9 epilogue.
 // Tile 128 x BN x 64; UMMA 128xBNx16, cta_group::1; kStages-deep smem ring (SWIZZLE_128B); two TMEM accumulator
 // stages so the epilogue of tile i overlaps the MMAs of tile i+1. Grid = #SMs, static round-robin tile order with
 // N fastest so the CTAs running together share A row-blocks through L2.
@@ -19,7 +19,8 @@ namespace kocr {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 
 template <int BN>
 struct GemmSmem {
@@ -33,9 +34,29 @@ struct GemmSmem {
   static constexpr int kTmemCols = 2 * kAccStride;
 };
 
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(1.702 x) and x * sigmoid(x) with MUFU ex2 + rcp (no IEEE-division slow path: the epilogue must stay
+// branch-free so the 32 elements of a chunk overlap their MUFU latencies). Error ~1e-6 relative, far below bf16.
+__device__ __forceinline__ float quick_gelu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                      pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -68,7 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -124,8 +145,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue: 8 warps, TMEM -> regs -> global.
+    // Warp w may touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane quarter split the tile's columns.
+    // Everything that does not depend on the accumulator (residual, RoPE angles) is fetched BEFORE the tmem_full wait,
+    // and the TMEM load of chunk c+1 is in flight while chunk c is processed, so the 1-2 warps per scheduler are not
+    // serialised on load latencies.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int acc = tl & 1;
@@ -133,113 +159,160 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + acc * S::kAccStride + ((uint32_t)(q * 32) << 16);
 
       if constexpr (EPI == kEpiQkvRope) {
-        // BN == 240: [q_h | k_h | v_h] of one head, 80 columns each (weights prepacked in that order).
+        // BN == 240 = [q_h | k_h | v_h] of one head (weights prepacked in that order).
+        // half 0: q (RoPE, pre-scale) + v[0:40);  half 1: k (RoPE) + v[40:80).
         const int2 pos = row_ok ? ep.pos_hw[row] : make_int2(0, 0);
-        const float2* cs_r = ep.rope_cs + (size_t)pos.x * 20;
-        const float2* cs_c = ep.rope_cs + (size_t)pos.y * 20;
-        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0;
-        const float* brow = ep.bias + n0;
-#pragma unroll 1
-        for (int sct = 0; sct < 3; ++sct) {
-          const float mul = (sct == 0) ? ep.q_scale : 1.0f;
+        float2 cs[40];  // (cos, sin) of the 40 distinct angles: j < 20 from the row position, else the column position
+        {
+          const float4* pr = reinterpret_cast<const float4*>(ep.rope_cs + (size_t)pos.x * 20);
+          const float4* pc = reinterpret_cast<const float4*>(ep.rope_cs + (size_t)pos.y * 20);
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            uint32_t a[8], b[8];
-            tmem_ld_x8(t_row + sct * 80 + c * 8, a);
-            tmem_ld_x8(t_row + sct * 80 + 40 + c * 8, b);
-            tc_wait_ld();
-            float lo[8], hi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = c * 8 + i;
-              const float x1 = __uint_as_float(a[i]) + __ldg(brow + sct * 80 + j);
-              const float x2 = __uint_as_float(b[i]) + __ldg(brow + sct * 80 + 40 + j);
-              if (sct < 2) {
-                const float2 cs = (j < 20) ? __ldg(cs_r + j) : __ldg(cs_c + (j - 20));
-                lo[i] = (x1 * cs.x - x2 * cs.y) * mul;
-                hi[i] = (x2 * cs.x + x1 * cs.y) * mul;
-              } else {
-                lo[i] = x1;
-                hi[i] = x2;
-              }
-            }
-            if (row_ok) {
-              uint4 v0 = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]),
-                                    pack_bf16(lo[6], lo[7]));
-              uint4 v1 = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]),
-                                    pack_bf16(hi[6], hi[7]));
-              *reinterpret_cast<uint4*>(orow + sct * 80 + c * 8) = v0;
-              *reinterpret_cast<uint4*>(orow + sct * 80 + 40 + c * 8) = v1;
-            }
+          for (int i = 0; i < 10; ++i) {
+            const float4 a = __ldg(pr + i), b = __ldg(pc + i);
+            cs[2 * i] = make_float2(a.x, a.y);
+            cs[2 * i + 1] = make_float2(a.z, a.w);
+            cs[20 + 2 * i] = make_float2(b.x, b.y);
+            cs[20 + 2 * i + 1] = make_float2(b.z, b.w);
           }
         }
-      } else if constexpr (EPI == KOCR_EPI_BIAS_SWIGLU) {
-        // accumulator columns alternate gate_j, up_j; output column j = silu(gate)*up; output width N/2
-        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0 / 2;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (n0 + c * 32 >= N) break;
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c * 32, r);
-          tc_wait_ld();
-          float o[16];
+        const float mul = (half == 0) ? ep.q_scale : 1.0f;
+        const int c_qk = half * 80;         // accumulator column of this half's rotated slot
+        const int c_v = 160 + half * 40;    // and of its share of v
+        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0;
+        const float* brow = ep.bias + n0;
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        uint32_t a[2][8], b[2][8];
+        tmem_ld_x8(t_row + c_qk, a[0]);
+        tmem_ld_x8(t_row + c_qk + 40, b[0]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float g = __uint_as_float(r[2 * i]) + __ldg(ep.bias + n0 + c * 32 + 2 * i);
-            const float u = __uint_as_float(r[2 * i + 1]) + __ldg(ep.bias + n0 + c * 32 + 2 * i + 1);
-            o[i] = silu(g) * u;
+        for (int c = 0; c < 5; ++c) {
+          tc_wait_ld();
+          if (c + 1 < 5) {
+            tmem_ld_x8(t_row + c_qk + (c + 1) * 8, a[(c + 1) & 1]);
+            tmem_ld_x8(t_row + c_qk + 40 + (c + 1) * 8, b[(c + 1) & 1]);
+          } else {
+            tmem_ld_x8(t_row + c_v, a[(c + 1) & 1]);
+            tmem_ld_x8(t_row + c_v + 8, b[(c + 1) & 1]);
+          }
+          const float4 b1a = __ldg(reinterpret_cast<const float4*>(brow + c_qk + c * 8));
+          const float4 b1b = __ldg(reinterpret_cast<const float4*>(brow + c_qk + c * 8 + 4));
+          const float4 b2a = __ldg(reinterpret_cast<const float4*>(brow + c_qk + 40 + c * 8));
+          const float4 b2b = __ldg(reinterpret_cast<const float4*>(brow + c_qk + 40 + c * 8 + 4));
+          const float bb1[8] = {b1a.x, b1a.y, b1a.z, b1a.w, b1b.x, b1b.y, b1b.z, b1b.w};
+          const float bb2[8] = {b2a.x, b2a.y, b2a.z, b2a.w, b2b.x, b2b.y, b2b.z, b2b.w};
+          float lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x1 = __uint_as_float(a[c & 1][i]) + bb1[i];
+            const float x2 = __uint_as_float(b[c & 1][i]) + bb2[i];
+            const float2 t = cs[c * 8 + i];
+            lo[i] = (x1 * t.x - x2 * t.y) * mul;
+            hi[i] = (x2 * t.x + x1 * t.y) * mul;
           }
           if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
-            dst[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            dst[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]),
-                                pack_bf16(o[14], o[15]));
+            *reinterpret_cast<uint4*>(orow + c_qk + c * 8) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
+                                                                        pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+            *reinterpret_cast<uint4*>(orow + c_qk + 40 + c * 8) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]),
+                                                                             pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+          }
+        }
+        // v share: 40 columns = 5 x8 loads; the first two are already in flight in a[1], b[1] (5 & 1 == 1)
+        uint32_t v2[3][8];
+        tc_wait_ld();
+        tmem_ld_x8(t_row + c_v + 16, v2[0]);
+        tmem_ld_x8(t_row + c_v + 24, v2[1]);
+        tmem_ld_x8(t_row + c_v + 32, v2[2]);
+        float vb[40];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(brow + c_v) + i);
+          vb[4 * i] = t.x; vb[4 * i + 1] = t.y; vb[4 * i + 2] = t.z; vb[4 * i + 3] = t.w;
+        }
+        tc_wait_ld();
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c_v);
+          const uint32_t* src[5] = {a[1], b[1], v2[0], v2[1], v2[2]};
+#pragma unroll
+          for (int g = 0; g < 5; ++g) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(src[g][i]) + vb[g * 8 + i];
+            dst[g] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
           }
         }
       } else {
-        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + n0;
-        const __nv_bfloat16* rrow = ep.residual + (size_t)row * ep.ld_res + n0;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (n0 + c * 32 >= N) break;  // N is a multiple of 32
-          uint32_t r[32];
-          tmem_ld_x32(t_row + c * 32, r);
-          uint4 res[4];
-          if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
-            if (row_ok) {
+        constexpr bool kSwiglu = EPI == KOCR_EPI_BIAS_SWIGLU;
+        constexpr int kChunks = BN / 32 / 2;  // chunks of 32 accumulator columns per half
+        const int col0 = n0 + half * (BN / 2);
+        int nch = (N - col0 + 31) / 32;
+        nch = nch < 0 ? 0 : (nch > kChunks ? kChunks : nch);
+        __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + (kSwiglu ? col0 / 2 : col0);
+        const __nv_bfloat16* rrow = ep.residual + (size_t)row * ep.ld_res + col0;
+        uint4 res[2][4];
+        if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
+          if (row_ok && nch > 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) res[i] = *(reinterpret_cast<const uint4*>(rrow + c * 32) + i);
-            }
+            for (int i = 0; i < 4; ++i) res[0][i] = *(reinterpret_cast<const uint4*>(rrow) + i);
           }
+        }
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld_x32(t_row + half * (BN / 2), r[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
           tc_wait_ld();
-          float v[32];
+          if (c + 1 < kChunks) tmem_ld_x32(t_row + half * (BN / 2) + (c + 1) * 32, r[(c + 1) & 1]);
+          if (c < nch) {
+            if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
+              if (row_ok && c + 1 < nch) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[i]);
-            if constexpr (EPI != KOCR_EPI_NONE) x += __ldg(ep.bias + n0 + c * 32 + i);
-            if constexpr (EPI == KOCR_EPI_BIAS_QUICKGELU) x = quick_gelu(x);
-            if constexpr (EPI == KOCR_EPI_BIAS_GELU) x = gelu_erf(x);
-            v[i] = x;
-          }
-          if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[2 * i] += bf16_lo(rw[i]);
-              v[2 * i + 1] += bf16_hi(rw[i]);
+                for (int i = 0; i < 4; ++i) res[(c + 1) & 1][i] = *(reinterpret_cast<const uint4*>(rrow + (c + 1) * 32) + i);
+              }
             }
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+            float v[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            for (int i = 0; i < 8; ++i) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (EPI != KOCR_EPI_NONE) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c * 32) + i);
+              v[4 * i] = __uint_as_float(r[c & 1][4 * i]) + bv.x;
+              v[4 * i + 1] = __uint_as_float(r[c & 1][4 * i + 1]) + bv.y;
+              v[4 * i + 2] = __uint_as_float(r[c & 1][4 * i + 2]) + bv.z;
+              v[4 * i + 3] = __uint_as_float(r[c & 1][4 * i + 3]) + bv.w;
+            }
+            if constexpr (EPI == KOCR_EPI_BIAS_QUICKGELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+            }
+            if constexpr (EPI == KOCR_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(res[c & 1]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[2 * i] += bf16_lo(rw[i]);
+                v[2 * i + 1] += bf16_hi(rw[i]);
+              }
+            }
+            if constexpr (kSwiglu) {
+              // accumulator columns alternate gate_j, up_j; output column j = silu(gate) * up (output width N/2)
+              float o[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = silu(v[2 * i]) * v[2 * i + 1];
+              if (row_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+                dst[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                dst[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+              }
+            } else {
+              if (row_ok) store_bf16x32(orow + c * 32, v);
+            }
           }
         }
       }
