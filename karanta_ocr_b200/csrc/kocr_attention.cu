@@ -9,13 +9,15 @@
 //
 // CTA = one 256-row query block of one sequence and one head; 384 threads:
 //   warp 0      TMA producer: Q once, then a ring of K tiles and a ring of V tiles (128 keys each)
-//   warp 1      MMA issuer:   S_t = Q_t K^T (128x128x80, SS) and O_t += P_t V (128x80x128, P from TMEM, V MN-major)
+//   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (SS) and O_t += P_t V (P from TMEM, V MN-major)
 //   warps 4-7   softmax of query tile 0 (rows 0..127), one row per thread
 //   warps 8-11  softmax of query tile 1 (rows 128..255)
 // Operand tiles are stored as five [128 rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
 // Q/K (K = head_dim) and, unchanged, a canonical MN-major layout for V (N = head_dim): no transpose, no padding of 80.
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,336) O1 [384,464); P_t (bf16) overwrites the first 64 columns of S_t.
-// The two query tiles ping-pong on the tensor pipe: while softmax works on S_0 the pipe runs P_1 V and the next S_1.
+// Scores are produced in 64-key sub-steps and double-buffered in TMEM per query tile (S[t][b], b = sub-step parity), so
+// S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe and the
+// kernel runs at the MUFU (ex2) rate, which is the binding unit for head_dim 80.
+// TMEM: S[t][b] at t*128 + b*64 (64 columns); P[t][b] (bf16) overwrites the first 32 columns of S[t][b]; O_t at 256 + t*128.
 #include <algorithm>
 #include <vector>
 
@@ -27,11 +29,13 @@ namespace kocr {
 static constexpr int kHd = 80;
 static constexpr int kChunks = kHd / 16;           // 5 chunks of 16 columns
 static constexpr int kTileRows = 128;
+static constexpr int kSub = 64;              // keys per score sub-step (S and P are double-buffered per query tile)
 static constexpr int kChunkBytes = kTileRows * 32;  // 4096
 static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
 static constexpr int kKvStages = 3;
 static constexpr int kAttnThreads = 384;
 static constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKvStages * kTileBytes + 512 + 1024;
+static constexpr int kPolyEvery = 4;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the row max grows by more than 2^8
 
 __device__ __forceinline__ float ex2(float x) {
@@ -64,6 +68,35 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 2^x for a pair of x <= 0 without the MUFU unit: x = n + r, n = round(x) via the 1.5*2^23 trick, 2^r by a degree-3
+// minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), then n is added
+// into the exponent field. x is clamped at -126 so the result never leaves the normal range (masked scores are -inf).
+__device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t xc = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t t2 = add_f32x2(xc, magic);                                    // low mantissa bits = round(x)
+  const uint64_t n2 = add_f32x2(t2, pack_f32x2(-12582912.0f, -12582912.0f));   // round(x) as a float
+  const uint64_t r2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), xc);             // r in [-0.5, 0.5]
+  uint64_t p2 = fma_f32x2(r2, pack_f32x2(0.055171649903059006f, 0.055171649903059006f), pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
+  p2 = fma_f32x2(p2, r2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  p2 = fma_f32x2(p2, r2, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(p2, p0, p1);
+  unpack_f32x2(t2, t0, t1);
+  const uint32_t b0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  const uint32_t b1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+  return pack_u32x2(b0, b1);
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                  const AttnWork* __restrict__ work, int num_heads) {
@@ -78,16 +111,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   uint64_t* k_empty = k_full + kKvStages;  // kKvStages
   uint64_t* v_full = k_empty + kKvStages;
   uint64_t* v_empty = v_full + kKvStages;
-  uint64_t* s_full = v_empty + kKvStages;  // 2
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = v_empty + kKvStages;  // [tile][buffer] = 4
+  uint64_t* p_full = s_full + 4;           // [tile][buffer] = 4
+  uint64_t* o_done = p_full + 4;           // [tile][sub-step parity] = 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const AttnWork w = work[blockIdx.x];
   const int head = blockIdx.y;
-  const int n_kv = (w.kv_len + kTileRows - 1) / kTileRows;
+  const int n_kv = (w.kv_len + kTileRows - 1) / kTileRows;  // 128-key smem tiles
+  const int n_sub = (w.kv_len + kSub - 1) / kSub;           // 64-key score sub-steps
   const int col_q = head * 3 * kHd, col_k = col_q + kHd, col_v = col_q + 2 * kHd;
 
   if (warp == 0 && lane == 0) {
@@ -95,11 +129,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     mbar_init(q_full, 1);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], 2);  // one tcgen05.commit from each query tile's MMA warp
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], 2);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 4; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 128);
       mbar_init(&o_done[t], 1);
@@ -111,81 +145,97 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S[t][b] (64 f32 columns, b = sub-step parity) at t*128 + b*64; P[t][b] (bf16 pairs) overwrites the
+  // first 32 columns of S[t][b]; O[t] (80 columns) at 256 + t*128.
 
   if (warp < 4) {
     setmaxnreg_dec<96>();
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      mbar_expect_tx(q_full, 2 * kTileBytes);
-      for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_qkv, q_full, col_q + c * 16,
-                      w.q_begin + t * kTileRows);
-      for (int j = 0; j < n_kv; ++j) {
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane issues)
+      const int q_begin = (int)uniform_u32(w.q_begin), kv_begin = (int)uniform_u32(w.kv_begin);
+      const int n_kv_u = (int)uniform_u32(n_kv);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        for (int t = 0; t < 2; ++t)
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_qkv, q_full, col_q + c * 16, q_begin + t * kTileRows);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv_u; ++j) {
         const int s = j % kKvStages;
         const uint32_t ph = (j / kKvStages) & 1;
-        const int row = w.kv_begin + j * kTileRows;
+        const int row = kv_begin + j * kTileRows;
         mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], kTileBytes);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_2d(smem_k + s * kTileBytes + c * kChunkBytes, &tm_qkv, &k_full[s], col_k + c * 16, row);
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[s], kTileBytes);
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_k + s * kTileBytes + c * kChunkBytes, &tm_qkv, &k_full[s], col_k + c * 16, row);
+        }
+        __syncwarp();
         mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], kTileBytes);
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_2d(smem_v + s * kTileBytes + c * kChunkBytes, &tm_qkv, &v_full[s], col_v + c * 16, row);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[s], kTileBytes);
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_v + s * kTileBytes + c * kChunkBytes, &tm_qkv, &v_full[s], col_v + c * 16, row);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+    } else if (warp == 1 || warp == 2) {
+      // ---------------------------------------------------------------- MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
+      // (warp-uniform loops, elected lane issues). Scores are double-buffered per query tile: S_t(i+2) is issued right
+      // after P_t(i).V, two sub-steps ahead of the softmax that will read it, so the softmax warps do not wait for the
+      // tensor pipe. One issuing warp per tile: a single warp could not keep up with 18 MMAs per 64-key sub-step.
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);  // Q (K-major) x K (K-major), 64 keys
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd, 0, 1);   // P (TMEM) x V (MN-major)
-      auto issue_s = [&](int t, int s) {
-        const uint32_t qa = smem_u32(smem_q + t * kTileBytes), ka = smem_u32(smem_k + s * kTileBytes);
+      constexpr uint32_t hi32 = smem_desc_hi(256, 6);                 // SWIZZLE_32B, 8-row groups 256 B apart
+      const int t = warp - 1;
+      const uint32_t tmem_u = uniform_u32(tmem_base);
+      const int n_sub_u = (int)uniform_u32(n_sub);
+      const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16) + t * (kTileBytes >> 4);
+      const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
+      const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kChunkBytes);  // LBO = distance between 16-column groups
+      const uint32_t d_o = tmem_u + 256 + t * 128;
+      auto issue_s = [&](int i) {
+        const int s = (i >> 1) % kKvStages;
+        const uint32_t ka = k_lo + s * (kTileBytes >> 4) + (i & 1) * ((kSub * 32) >> 4);
+        const uint32_t d = tmem_u + t * 128 + (i & 1) * kSub;
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          const uint64_t da = make_smem_desc(qa + c * kChunkBytes, 16, 256, 6);
-          const uint64_t db = make_smem_desc(ka + c * kChunkBytes, 16, 256, 6);
-          umma_ss(tmem_base + t * 128, da, db, idesc_s, c != 0);
-        }
+        for (int c = 0; c < kChunks; ++c)
+          umma_ss_lo(d, q_lo + c * (kChunkBytes >> 4), ka + c * (kChunkBytes >> 4), hi32, idesc_s, c != 0);
+        tc_commit_elect(&s_full[t * 2 + (i & 1)]);
       };
-      auto issue_pv = [&](int t, int s, bool accumulate) {
-        const uint32_t va = smem_u32(smem_v + s * kTileBytes);
+      auto issue_pv = [&](int i) {
+        const int s = (i >> 1) % kKvStages;
+        const uint32_t va = v_lo + s * (kTileBytes >> 4) + (i & 1) * ((kSub * 32) >> 4);
+        const uint32_t pa = tmem_u + t * 128 + (i & 1) * kSub;
 #pragma unroll
-        for (int ks = 0; ks < kTileRows / 16; ++ks) {
-          // 16 keys per step: rows ks*16.. of every chunk (512 B further); N groups of 16 columns are 4096 B apart
-          const uint64_t db = make_smem_desc(va + ks * 512, kChunkBytes, 256, 6);
-          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8, db, idesc_o, (accumulate || ks != 0));
-        }
+        for (int ks = 0; ks < kSub / 16; ++ks)  // 16 keys per step: rows ks*16.. of every chunk, 512 B further
+          umma_ts_lo(d_o, pa + ks * 8, va + ks * (512 >> 4), hi32, idesc_o, (i > 0 || ks != 0));
+        tc_commit_elect(&o_done[t * 2 + (i & 1)]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      tc_commit(&s_full[0]);
-      issue_s(1, 0);
-      tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        const int s1 = (j + 1) % kKvStages;
-        const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
-        mbar_wait(&v_full[s], ph);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          tc_fence_after();
-          issue_pv(t, s, j > 0);
-          tc_commit(&o_done[t]);
-          if (j + 1 < n_kv) {
-            if (t == 0) {
-              mbar_wait(&k_full[s1], ph1);
-              tc_fence_after();
-            }
-            issue_s(t, s1);
-            tc_commit(&s_full[t]);
-            if (t == 1) tc_commit(&k_empty[s1]);
+      issue_s(0);
+      if (n_sub_u > 1) issue_s(1);
+      tc_commit_elect(&k_empty[0]);
+      for (int i = 0; i < n_sub_u; ++i) {
+        const int kt = i >> 1;
+        if ((i & 1) == 0) mbar_wait(&v_full[kt % kKvStages], (kt / kKvStages) & 1);
+        mbar_wait(&p_full[t * 2 + (i & 1)], (i >> 1) & 1);
+        tc_fence_after();
+        issue_pv(i);
+        const int i2 = i + 2;
+        if (i2 < n_sub_u) {
+          const int kt2 = i2 >> 1;
+          if ((i2 & 1) == 0) {
+            mbar_wait(&k_full[kt2 % kKvStages], (kt2 / kKvStages) & 1);
+            tc_fence_after();
           }
+          issue_s(i2);
+          if ((i2 & 1) == 1 || i2 == n_sub_u - 1) tc_commit_elect(&k_empty[kt2 % kKvStages]);
         }
-        tc_commit(&v_empty[s]);
+        if ((i & 1) == 1 || i == n_sub_u - 1) tc_commit_elect(&v_empty[kt % kKvStages]);
       }
     }
   } else {
@@ -195,50 +245,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     const int qtr = warp & 3;        // TMEM lane quarter
     const int r = qtr * 32 + lane;   // row within the tile
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    const uint32_t t_s = tmem_base + t * 128 + lane_off;
     const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
     float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
+    for (int i = 0; i < n_sub; ++i) {
+      const uint32_t t_s = tmem_base + t * 128 + (i & 1) * kSub + lane_off;
+      mbar_wait(&s_full[t * 2 + (i & 1)], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t sr[128];
+      uint32_t sr[kSub];
       tmem_ld_x32(t_s, sr);
       tmem_ld_x32(t_s + 32, sr + 32);
-      tmem_ld_x32(t_s + 64, sr + 64);
-      tmem_ld_x32(t_s + 96, sr + 96);
       tc_wait_ld();
-      const int valid = w.kv_len - j * kTileRows;
-      if (valid < kTileRows) {
+      const int valid = w.kv_len - i * kSub;
+      if (valid < kSub) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
+        for (int c = 0; c < kSub; ++c)
           if (c >= valid) sr[c] = 0xff800000u;  // -inf
       }
-      // row max: 4 independent FMNMX3 chains (a single chain of 127 dependent max ops would cost ~500 cycles)
+      // row max: 4 independent FMNMX3 chains
       float mxa[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        mxa[g] = max3(__uint_as_float(sr[32 * g]), __uint_as_float(sr[32 * g + 1]), __uint_as_float(sr[32 * g + 2]));
+        mxa[g] = max3(__uint_as_float(sr[16 * g]), __uint_as_float(sr[16 * g + 1]), __uint_as_float(sr[16 * g + 2]));
 #pragma unroll
-        for (int c = 3; c < 31; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[32 * g + c]), __uint_as_float(sr[32 * g + c + 1]));
-        mxa[g] = fmaxf(mxa[g], __uint_as_float(sr[32 * g + 31]));
+        for (int c = 3; c < 15; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[16 * g + c]), __uint_as_float(sr[16 * g + c + 1]));
+        mxa[g] = fmaxf(mxa[g], __uint_as_float(sr[16 * g + 15]));
       }
       const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       float alpha = 1.0f;
-      const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first tile (m_ref = -inf)
+      const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first sub-step (m_ref = -inf)
       if (grow) {
-        alpha = ex2(m_ref - mx);  // 0 on the first tile
+        alpha = ex2(m_ref - mx);  // 0 on the first sub-step
         m_ref = mx;
       }
       // p = 2^(s - m): packed f32x2 subtract and 4 independent packed row-sum accumulators
       const uint64_t neg_m2 = pack_f32x2(-m_ref, -m_ref);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[64];
+      uint32_t pk[kSub / 2];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float x0, x1;
-        unpack_f32x2(add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2), x0, x1);
-        const float p0 = ex2(x0), p1 = ex2(x1);
-        acc2[c & 3] = add_f32x2(acc2[c & 3], pack_f32x2(p0, p1));
+      for (int c = 0; c < kSub / 2; ++c) {
+        const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
+        uint64_t p2;
+        if (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) {
+          p2 = ex2_poly_f32x2(x2);  // FMA/ALU pipes: relieves the MUFU unit, which is the binding pipe at head_dim 80
+        } else {
+          float x0, x1;
+          unpack_f32x2(x2, x0, x1);
+          p2 = pack_f32x2(ex2(x0), ex2(x1));
+        }
+        acc2[c & 3] = add_f32x2(acc2[c & 3], p2);
+        float p0, p1;
+        unpack_f32x2(p2, p0, p1);
         pk[c] = pack_bf16(p0, p1);
       }
       float sum;
@@ -251,12 +307,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       l = l * alpha + sum;
       tmem_st_x16(t_s, pk);
       tmem_st_x16(t_s + 16, pk + 16);
-      tmem_st_x16(t_s + 32, pk + 32);
-      tmem_st_x16(t_s + 48, pk + 48);
-      if (j > 0) {
-        // O_t holds P V of tiles < j relative to the old reference; bring it to the new one before P_j V is added
+      // P.V completions are signalled on two alternating barriers per tile, o_done[t][i&1], so a parity wait stays
+      // unambiguous as long as every completion is observed within two sub-steps. P_{i-2} V (issued two softmaxes ago)
+      // is observed here every sub-step - normally free - and P_{i-1} V only when O really has to be rescaled.
+      if (i > 1) mbar_wait(&o_done[t * 2 + (i & 1)], ((i - 2) >> 1) & 1);
+      if (i > 0) {
+        // O_t holds P V of sub-steps < i relative to the old reference; bring it to the new one before P_i V is added
         if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&o_done[t], (j - 1) & 1);
+          mbar_wait(&o_done[t * 2 + ((i - 1) & 1)], ((i - 1) >> 1) & 1);
           tc_fence_after();
           uint32_t o[80];
 #pragma unroll
@@ -270,10 +328,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      mbar_arrive(&p_full[t * 2 + (i & 1)]);
     }
     // ---- epilogue: O / l -> bf16 -> out[row, head*80 ..]
-    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    if (n_sub > 1) mbar_wait(&o_done[t * 2 + ((n_sub - 2) & 1)], ((n_sub - 2) >> 1) & 1);
+    mbar_wait(&o_done[t * 2 + ((n_sub - 1) & 1)], ((n_sub - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t o[80];
 #pragma unroll

@@ -73,7 +73,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
@@ -100,49 +100,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
-          const int s = it % S::kStages;
-          const uint32_t ph = (it / S::kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      for (int kb = 0; kb < num_k; ++kb, ++it) {
+        const int s = it % S::kStages;
+        const uint32_t ph = (it / S::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], S::kStageBytes);
           tma_load_2d(smem_a + s * S::kABytes, &tm_a, &full_bar[s], kb * BK, m0);
           tma_load_2d(smem_b + s * S::kBBytes, &tm_b, &full_bar[s], kb * BK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-        const int acc = tl & 1;
-        const uint32_t acc_ph = (tl >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t desc_hi = smem_desc_hi(1024, 2);  // SWIZZLE_128B, 8-row groups 1024 B apart
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem_a), 16);
+    const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem_b), 16);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    uint32_t it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int acc = tl & 1;
+      const uint32_t acc_ph = (tl >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + acc * S::kAccStride;
+      for (int kb = 0; kb < num_k; ++kb, ++it) {
+        const int s = it % S::kStages;
+        const uint32_t ph = (it / S::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * S::kAccStride;
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
-          const int s = it % S::kStages;
-          const uint32_t ph = (it / S::kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + s * S::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + s * S::kBBytes);
+        const uint32_t a_lo = a_lo0 + s * (S::kABytes >> 4);
+        const uint32_t b_lo = b_lo0 + s * (S::kBBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
-          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-        }
-        tc_commit(&tmem_full[acc]);  // accumulator complete
+        for (int k = 0; k < BK / 16; ++k) umma_ss_lo(d_tmem, a_lo + k * 2, b_lo + k * 2, desc_hi, idesc, (kb | k) != 0);
+        tc_commit_elect(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
       }
+      tc_commit_elect(&tmem_full[acc]);  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 8 warps, TMEM -> regs -> global.
@@ -265,6 +264,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         tmem_ld_x32(t_row + half * (BN / 2), r[0]);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
+          // bias of this chunk is fetched before the TMEM wait so both latencies overlap
+          float4 bv[8];
+          if constexpr (EPI != KOCR_EPI_NONE) {
+            if (c < nch) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c * 32) + i);
+            }
+          }
           tc_wait_ld();
           if (c + 1 < kChunks) tmem_ld_x32(t_row + half * (BN / 2) + (c + 1) * 32, r[(c + 1) & 1]);
           if (c < nch) {
@@ -277,12 +284,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             float v[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if constexpr (EPI != KOCR_EPI_NONE) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c * 32) + i);
-              v[4 * i] = __uint_as_float(r[c & 1][4 * i]) + bv.x;
-              v[4 * i + 1] = __uint_as_float(r[c & 1][4 * i + 1]) + bv.y;
-              v[4 * i + 2] = __uint_as_float(r[c & 1][4 * i + 2]) + bv.z;
-              v[4 * i + 3] = __uint_as_float(r[c & 1][4 * i + 3]) + bv.w;
+              if constexpr (EPI == KOCR_EPI_NONE) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * i] = __uint_as_float(r[c & 1][4 * i]) + bv[i].x;
+              v[4 * i + 1] = __uint_as_float(r[c & 1][4 * i + 1]) + bv[i].y;
+              v[4 * i + 2] = __uint_as_float(r[c & 1][4 * i + 2]) + bv[i].z;
+              v[4 * i + 3] = __uint_as_float(r[c & 1][4 * i + 3]) + bv[i].w;
             }
             if constexpr (EPI == KOCR_EPI_BIAS_QUICKGELU) {
 #pragma unroll

@@ -25,6 +25,9 @@ struct PageJob {
   const int32_t* vb;  // vertical bounds [out_h][2], or null
   const int32_t* vc;  // vertical coeffs [out_h][vk]
   long long token_base;
+  long long chan_stride;  // bytes between channels of one pixel (0 for gray: do_convert_rgb replicates)
+  int row_pitch;          // bytes between rows
+  int pix_stride;         // bytes between horizontally adjacent pixels
   int in_h, in_w, layout;
   int out_h, out_w;
   int hk, hprec, vk, vprec;
@@ -34,17 +37,16 @@ struct PageJob {
 static constexpr int kStrip = 28;       // output rows per tile = patch * merge
 static constexpr int kPatchDim = 1176;  // 3 * 2 * 14 * 14
 static constexpr int kThreads = 256;
+static constexpr int kRB = 14;           // rows of horizontal-pass accumulators held in registers per thread
 
 __device__ __forceinline__ uint8_t load_px(const PageJob& j, int c, int r, int x) {
-  if (j.layout == KOCR_LAYOUT_CHW) return __ldg(j.src + ((size_t)c * j.in_h + r) * j.in_w + x);
-  if (j.layout == KOCR_LAYOUT_HWC) return __ldg(j.src + ((size_t)r * j.in_w + x) * 3 + c);
-  return __ldg(j.src + (size_t)r * j.in_w + x);
+  return __ldg(j.src + c * j.chan_stride + (long long)r * j.row_pitch + x * j.pix_stride);
 }
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kThreads) preprocess_kernel(const PageJob* __restrict__ jobs, int n_jobs,
+__global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* __restrict__ jobs, int n_jobs,
                                                               int n_tiles, const float* __restrict__ lut_g,
-                                                              void* __restrict__ out, int max_mid_bytes) {
+                                                              void* __restrict__ out, int max_mid_bytes, int coef_off) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float lut[768];
   __shared__ PageJob job;
@@ -75,24 +77,52 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(const PageJob* __r
     uint8_t* mid = smem;                                   // [3][rows_in][tw]
     uint8_t* res = j.vb ? smem + max_mid_bytes : smem;     // [3][28][tw]
 
-    // ---- phase 1: horizontal pass (or plain copy) into mid
-    const int n1 = 3 * rows_in * tw;
-    for (int i = threadIdx.x; i < n1; i += kThreads) {
-      const int x = i % tw;
-      const int rc = i / tw;
-      const int r = rc % rows_in, c = rc / rows_in;
-      const int xo = x0 + x;
-      uint8_t v;
-      if (j.hb) {
-        const int xmin = j.hb[2 * xo], cnt = j.hb[2 * xo + 1];
-        const int32_t* k = j.hc + (size_t)xo * j.hk;
-        int acc = 1 << (j.hprec - 1);
-        for (int t = 0; t < cnt; ++t) acc += (int)load_px(j, c, r0 + r, xmin + t) * k[t];
-        v = (uint8_t)min(max(acc >> j.hprec, 0), 255);
-      } else {
-        v = load_px(j, c, r0 + r, xo);
+    // ---- phase 1: horizontal pass (or plain copy) into mid. One thread per output column: its tap window and
+    // coefficients are read once, then reused for every row and channel (kRB rows of accumulators in registers);
+    // consecutive threads read consecutive input bytes of the same row.
+    if (j.hb) {
+      int32_t* kcoef = reinterpret_cast<int32_t*>(smem + coef_off);  // [hk][tw] transposed: conflict-free
+      for (int i = threadIdx.x; i < j.hk * tw; i += kThreads) {
+        const int t = i / tw, x = i % tw;
+        kcoef[i] = j.hc[(size_t)(x0 + x) * j.hk + t];
       }
-      mid[i] = v;
+      __syncthreads();
+      const int x = threadIdx.x;
+      if (x < tw) {
+        const int xmin = j.hb[2 * (x0 + x)], cnt = j.hb[2 * (x0 + x) + 1];
+        const int round0 = 1 << (j.hprec - 1);
+        for (int rb = 0; rb < rows_in; rb += kRB) {
+          int acc[3][kRB];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) acc[c][r] = round0;
+          const uint8_t* col = j.src + (long long)(r0 + rb) * j.row_pitch + (long long)xmin * j.pix_stride;
+          const int nr = min(kRB, rows_in - rb);
+          for (int t = 0; t < cnt; ++t, col += j.pix_stride) {
+            const int kt = kcoef[t * tw + x];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const uint8_t* pc = col + c * j.chan_stride;
+#pragma unroll
+              for (int r = 0; r < kRB; ++r, pc += j.row_pitch)
+                if (r < nr) acc[c][r] += (int)__ldg(pc) * kt;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < kRB; ++r)
+              if (rb + r < rows_in) mid[((size_t)c * rows_in + rb + r) * tw + x] = (uint8_t)min(max(acc[c][r] >> j.hprec, 0), 255);
+        }
+      }
+    } else {
+      const int n1 = 3 * rows_in * tw;
+      for (int i = threadIdx.x; i < n1; i += kThreads) {
+        const int x = i % tw;
+        const int rc = i / tw;
+        mid[i] = load_px(j, rc / rows_in, r0 + rc % rows_in, x0 + x);
+      }
     }
     __syncthreads();
 
@@ -221,6 +251,9 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     memset(&j, 0, sizeof j);
     j.src = im.data;
     j.in_h = im.height; j.in_w = im.width; j.layout = im.layout;
+    if (im.layout == KOCR_LAYOUT_CHW) { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = (long long)im.height * im.width; }
+    else if (im.layout == KOCR_LAYOUT_HWC) { j.pix_stride = 3; j.row_pitch = 3 * im.width; j.chan_stride = 1; }
+    else { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = 0; }
     j.out_h = oh; j.out_w = ow;
     j.token_base = tokens;
     const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
@@ -275,18 +308,22 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   rc = ctx->stage_commit(slot, total, stream, &d);
   if (rc) return rc;
 
-  const int smem = max_mid + max_res;
+  int max_coef = 0;
+  for (int i = 0; i < n_images; ++i)
+    if (ht[i]) max_coef = std::max(max_coef, ht[i]->ksize * jobs[i].tile_w * 4);
+  const int coef_off = (max_mid + max_res + 15) & ~15;
+  const int smem = coef_off + max_coef;
   const int grid = std::min(tiles, ctx->num_sms * 8);
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
   ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
     KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                              pixel_values, max_mid);
+                                                              pixel_values, max_mid, coef_off);
   } else {
     KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                               pixel_values, max_mid);
+                                                               pixel_values, max_mid, coef_off);
   }
   KOCR_LAUNCH_CHECK("preprocess_kernel");
   return KOCR_OK;

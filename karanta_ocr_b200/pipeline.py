@@ -34,6 +34,33 @@ def shard_pages(costs, world_size: int):
     return [sorted(s) for s in shards]
 
 
+def gather_pages(local_items, local_indices, n_total: int, group=None, dst: int = 0):
+    """Host-side gather of per-page results in original page order (the reference routes whole pages to independent
+    engines and collects on the host: bulk_processing/workers/inference_worker.py:205-228). `local_items[k]` is the
+    result for page `local_indices[k]`. Returns the ordered list on rank `dst`, None elsewhere. Works on any
+    torch.distributed backend (objects travel through the CPU); without an initialised group it is the identity."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        out = [None] * n_total
+        for i, it in zip(local_indices, local_items):
+            out[i] = it
+        return out
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    payload = [(int(i), it.cpu() if hasattr(it, "cpu") else it) for i, it in zip(local_indices, local_items)]
+    buf = [None] * world if rank == dst else None
+    dist.gather_object(payload, buf, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = [None] * n_total
+    for part in buf:
+        for i, it in part:
+            out[i] = it
+    if any(o is None for o in out):
+        raise RuntimeError("gather_pages: some pages were not produced by any rank")
+    return out
+
+
 class PageEncoder:
     """processor + tower on one GPU. `encode(pages)` returns (embeddings bf16 [sum N / 4, out_hidden] on the GPU,
     image_grid_thw int64 [n, 3])."""
@@ -44,6 +71,23 @@ class PageEncoder:
         self.processor = KarantaImageProcessor(min_pixels=min_pixels, max_pixels=max_pixels, resize_backend=resize_backend,
                                                device=tower.device)
         self.last_launch_count = 0
+
+    @torch.no_grad()
+    def encode_sharded(self, pages, rank: int, world_size: int, batch_pages: int = 64):
+        """Encode this rank's LPT shard of `pages` (all ranks pass the same list); returns (per-page embeddings on the
+        host, page indices). Pair with gather_pages() for the host-side gather."""
+        minp, maxp = self.processor.min_pixels, self.processor.max_pixels
+        costs = []
+        for p in pages:
+            h, w = (p.height, p.width) if hasattr(p, "height") else (p.shape[-2:] if p.shape[0] in (1, 3, 4) and p.ndim == 3 else p.shape[:2])
+            costs.append(page_cost(int(h), int(w), minp, maxp))
+        mine = shard_pages(costs, world_size)[rank]
+        outs = []
+        for b in range(0, len(mine), batch_pages):
+            idx = mine[b:b + batch_pages]
+            emb, grid = self.encode([pages[i] for i in idx])
+            outs.extend(t.cpu() for t in self.tower.split_per_image(emb, grid))
+        return outs, mine
 
     @torch.no_grad()
     def encode(self, pages):

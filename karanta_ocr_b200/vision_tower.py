@@ -91,13 +91,13 @@ class KarantaVisionTower(torch.nn.Module):
         self.last_launch_count = 0
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            try:
+        try:
+            h = self.__dict__.get("_h")
+            if h is not None and h.value:
                 _lib.load().kocr_tower_destroy(h)
-            except Exception:
-                pass
-            self._h = None
+                h.value = None
+        except Exception:  # interpreter teardown
+            pass
 
     # ---- nn.Module-compatible surface the call sites touch
     @property
