@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkocr.so")
+LIB_PATH = os.environ.get("KOCR_LIB") or os.path.join(HERE, "libkocr.so")  # KOCR_LIB: A/B kernel variants in experiments
 
 OK, ERR_INVALID, ERR_ASPECT, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
 RESIZE_PIL, RESIZE_ATEN = 0, 1

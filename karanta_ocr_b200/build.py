@@ -20,6 +20,26 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def build_variant(name, defines):
+    """Experiment helper: build libkocr_<name>.so with extra -D flags (select it at run time with KOCR_LIB=<path>)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(HERE, f"libkocr_{name}.so")
+    d = os.path.join(HERE, "build", name)
+    os.makedirs(d, exist_ok=True)
+    objs, procs = [], []
+    for f in SOURCES:
+        o = os.path.join(d, f.replace(".cu", ".o"))
+        objs.append(o)
+        procs.append(subprocess.Popen([nvcc] + NVCC_FLAGS + [f"-D{x}" for x in defines] + ["-c", os.path.join(CSRC, f), "-o", o],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out_txt, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(out_txt)
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT

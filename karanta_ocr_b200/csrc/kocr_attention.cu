@@ -35,7 +35,13 @@ static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
 static constexpr int kKvStages = 3;
 static constexpr int kAttnThreads = 384;
 static constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKvStages * kTileBytes + 512 + 1024;
-static constexpr int kPolyEvery = 4;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
+#ifndef KOCR_POLY_EVERY
+#define KOCR_POLY_EVERY 4
+#endif
+#ifndef KOCR_PREFETCH_S
+#define KOCR_PREFETCH_S 0
+#endif
+static constexpr int kPolyEvery = KOCR_POLY_EVERY;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the row max grows by more than 2^8
 
 __device__ __forceinline__ float ex2(float x) {
@@ -247,14 +253,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
     const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
     float m_ref = -INFINITY, l = 0.f;
+#if KOCR_PREFETCH_S
+    uint32_t sr[kSub];
+    mbar_wait(&s_full[t * 2], 0);
+    tc_fence_after();
+    tmem_ld_x32(tmem_base + t * 128 + lane_off, sr);
+    tmem_ld_x32(tmem_base + t * 128 + lane_off + 32, sr + 32);
+#endif
     for (int i = 0; i < n_sub; ++i) {
       const uint32_t t_s = tmem_base + t * 128 + (i & 1) * kSub + lane_off;
+#if KOCR_PREFETCH_S
+      tc_wait_ld();  // S(i) was requested at the tail of the previous iteration
+#else
       mbar_wait(&s_full[t * 2 + (i & 1)], (i >> 1) & 1);
       tc_fence_after();
       uint32_t sr[kSub];
       tmem_ld_x32(t_s, sr);
       tmem_ld_x32(t_s + 32, sr + 32);
       tc_wait_ld();
+#endif
       const int valid = w.kv_len - i * kSub;
       if (valid < kSub) {
 #pragma unroll
@@ -307,6 +324,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       l = l * alpha + sum;
       tmem_st_x16(t_s, pk);
       tmem_st_x16(t_s + 16, pk + 16);
+#if KOCR_PREFETCH_S
+      // the score registers are dead: request S(i+1) now so its TMEM latency (and the s_full check) overlaps the
+      // P store, the O bookkeeping and the p_full hand-off below
+      if (i + 1 < n_sub) {
+        mbar_wait(&s_full[t * 2 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_n = tmem_base + t * 128 + ((i + 1) & 1) * kSub + lane_off;
+        tmem_ld_x32(t_n, sr);
+        tmem_ld_x32(t_n + 32, sr + 32);
+      }
+#endif
       // P.V completions are signalled on two alternating barriers per tile, o_done[t][i&1], so a parity wait stays
       // unambiguous as long as every completion is observed within two sub-steps. P_{i-2} V (issued two softmaxes ago)
       // is observed here every sub-step - normally free - and P_{i-1} V only when O really has to be rescaled.

@@ -50,12 +50,25 @@ __device__ __forceinline__ float quick_gelu(float x) { return x * rcp_approx(1.0
 __device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread's 64-byte share of a row is two full 32-byte
+// sectors, so each warp-level access touches 32 whole sectors instead of 32 half sectors (half the LSU transactions).
+__device__ __forceinline__ void stg_256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg_256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
+  uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    d[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                      pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  stg_256(dst, w);
+  stg_256(dst + 16, w + 8);
 }
 
 template <int BN, int EPI>
@@ -251,11 +264,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         nch = nch < 0 ? 0 : (nch > kChunks ? kChunks : nch);
         __nv_bfloat16* orow = ep.out + (size_t)row * ep.ldc + (kSwiglu ? col0 / 2 : col0);
         const __nv_bfloat16* rrow = ep.residual + (size_t)row * ep.ld_res + col0;
-        uint4 res[2][4];
+        uint32_t res[2][16];
         if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
           if (row_ok && nch > 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) res[0][i] = *(reinterpret_cast<const uint4*>(rrow) + i);
+            ldg_256(rrow, res[0]);
+            ldg_256(rrow + 16, res[0] + 8);
           }
         }
         mbar_wait(&tmem_full[acc], acc_ph);
@@ -277,8 +290,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           if (c < nch) {
             if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
               if (row_ok && c + 1 < nch) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) res[(c + 1) & 1][i] = *(reinterpret_cast<const uint4*>(rrow + (c + 1) * 32) + i);
+                ldg_256(rrow + (c + 1) * 32, res[(c + 1) & 1]);
+                ldg_256(rrow + (c + 1) * 32 + 16, res[(c + 1) & 1] + 8);
               }
             }
             float v[32];
@@ -299,7 +312,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
             if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL) {
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(res[c & 1]);
+              const uint32_t* rw = res[c & 1];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 v[2 * i] += bf16_lo(rw[i]);
@@ -312,9 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 16; ++i) o[i] = silu(v[2 * i]) * v[2 * i + 1];
               if (row_ok) {
-                uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
-                dst[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-                dst[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+                uint32_t w8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w8[i] = pack_bf16(o[2 * i], o[2 * i + 1]);
+                stg_256(orow + c * 16, w8);
               }
             } else {
               if (row_ok) store_bf16x32(orow + c * 32, v);
@@ -358,9 +372,12 @@ int launch_gemm(Ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb
                 int epi, const GemmEpilogue& ep, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(KOCR_ERR_INVALID, "gemm: non-positive dimension");
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(KOCR_ERR_UNSUPPORTED, "gemm: dimension over 2^31");
-  if (lda % 8 || ldb % 8 || ep.ldc % 8) return fail(KOCR_ERR_UNSUPPORTED, "gemm: row pitches must be multiples of 8 elements");
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(ep.out)) & 15)
-    return fail(KOCR_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned");
+  if (lda % 8 || ldb % 8 || ep.ldc % 16 || ep.ld_res % 16)
+    return fail(KOCR_ERR_UNSUPPORTED, "gemm: A/B row pitches must be multiples of 8 elements, C/residual pitches of 16");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)
+    return fail(KOCR_ERR_UNSUPPORTED, "gemm: A and B must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(ep.out) | reinterpret_cast<uintptr_t>(ep.residual)) & 31)
+    return fail(KOCR_ERR_UNSUPPORTED, "gemm: C and residual must be 32-byte aligned (256-bit epilogue accesses)");
   const int bn = (epi == kEpiQkvRope) ? 240 : 256;
   if (epi == kEpiQkvRope) {
     if (N % 240) return fail(KOCR_ERR_UNSUPPORTED, "gemm(qkv_rope): N must be a multiple of 240");

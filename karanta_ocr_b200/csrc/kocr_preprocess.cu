@@ -9,7 +9,8 @@
 //   tile  = (page, strip of 28 output rows = one merge row, chunk of tile_w output columns)
 //   phase 1 horizontal taps from global (L1-resident rows) -> smem mid[3][rows_in][tile_w]  (uint8)
 //   phase 2 vertical taps from smem                      -> smem res[3][28][tile_w]        (uint8)
-//   phase 3 LUT + patch-order gather from smem; a tile's tokens are one contiguous run of pixel_values.
+//   phase 3 LUT + patch-order gather smem -> smem; a tile's tokens are one contiguous span of pixel_values, which
+//           leaves the SM as a single cp.async.bulk (TMA engine) copy per tile.
 #include <map>
 #include <tuple>
 #include <vector>
@@ -25,6 +26,7 @@ struct PageJob {
   const int32_t* vb;  // vertical bounds [out_h][2], or null
   const int32_t* vc;  // vertical coeffs [out_h][vk]
   long long token_base;
+  long long src_bytes;    // size of the image buffer (staging never reads past it)
   long long chan_stride;  // bytes between channels of one pixel (0 for gray: do_convert_rgb replicates)
   int row_pitch;          // bytes between rows
   int pix_stride;         // bytes between horizontally adjacent pixels
@@ -39,6 +41,22 @@ static constexpr int kPatchDim = 1176;  // 3 * 2 * 14 * 14
 static constexpr int kThreads = 256;
 static constexpr int kRB = 14;           // rows of horizontal-pass accumulators held in registers per thread
 
+// 1-D bulk async copy shared -> global (TMA engine, no tensor map): size and both addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ uint8_t load_px(const PageJob& j, int c, int r, int x) {
   return __ldg(j.src + c * j.chan_stride + (long long)r * j.row_pitch + x * j.pix_stride);
 }
@@ -46,7 +64,7 @@ __device__ __forceinline__ uint8_t load_px(const PageJob& j, int c, int r, int x
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* __restrict__ jobs, int n_jobs,
                                                               int n_tiles, const float* __restrict__ lut_g,
-                                                              void* __restrict__ out, int max_mid_bytes, int coef_off) {
+                                                              void* __restrict__ out, int max_mid_bytes, int coef_off, int out_off) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float lut[768];
   __shared__ PageJob job;
@@ -77,51 +95,105 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     uint8_t* mid = smem;                                   // [3][rows_in][tw]
     uint8_t* res = j.vb ? smem + max_mid_bytes : smem;     // [3][28][tw]
 
-    // ---- phase 1: horizontal pass (or plain copy) into mid. One thread per output column: its tap window and
-    // coefficients are read once, then reused for every row and channel (kRB rows of accumulators in registers);
-    // consecutive threads read consecutive input bytes of the same row.
+    // ---- phase 0: stage the input rows of this tile in smem with aligned 32-bit loads, all in flight at once (one
+    // global-latency round trip per tile instead of one per filter tap). Rows are re-aligned on the way (funnel shift of
+    // two aligned words): row r of segment s starts exactly at stage + (s*rows_in + r)*Lp.
+    int xin0 = x0, ncols_in = tw;
+    if (j.hb) {
+      xin0 = j.hb[2 * x0];
+      ncols_in = j.hb[2 * (x0 + tw - 1)] + j.hb[2 * (x0 + tw - 1) + 1] - xin0;
+    }
+    const int nseg = j.layout == KOCR_LAYOUT_CHW ? 3 : 1;     // planar: one segment per channel; interleaved / gray: one
+    const int Lp = ((ncols_in * j.pix_stride + 6) & ~3) + 4;  // staged bytes per row, a multiple of 4
+    const int wpr = Lp >> 2;
+    uint8_t* stage = smem + out_off;  // aliases the output staging buffer (free until phase 3)
+    const uint8_t* seg0 = j.src + (long long)r0 * j.row_pitch + (long long)xin0 * j.pix_stride;
+    if (threadIdx.x == 0) bulk_store_wait_read();  // the previous tile's bulk copy has finished reading that buffer
+    __syncthreads();
+    {
+      const uintptr_t img_end = (reinterpret_cast<uintptr_t>(j.src) + j.src_bytes + 3) & ~uintptr_t(3);
+      uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
+      const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+      const int nrows = nseg * rows_in;
+      constexpr int kWarps = kThreads / 32, kRowsInFlight = 6;
+      // warp per staged row, lanes over its words; kRowsInFlight rows are requested before the first is consumed, and
+      // the upper word of each funnel shift comes from the neighbouring lane instead of a second load
+      for (int wd0 = 0; wd0 < wpr; wd0 += 32) {
+        const int wd = wd0 + lane;
+        for (int sr0 = wrp; sr0 < nrows; sr0 += kWarps * kRowsInFlight) {
+          uint32_t lo[kRowsInFlight], nx[kRowsInFlight];
+          int sh[kRowsInFlight];
+#pragma unroll
+          for (int b = 0; b < kRowsInFlight; ++b) {
+            const int sr = sr0 + b * kWarps;
+            lo[b] = nx[b] = 0u;
+            sh[b] = 0;
+            if (sr < nrows) {
+              const int sg = sr >= 2 * rows_in ? 2 : (sr >= rows_in ? 1 : 0);
+              const uintptr_t p = reinterpret_cast<uintptr_t>(seg0 + sg * j.chan_stride + (long long)(sr - sg * rows_in) * j.row_pitch);
+              const uintptr_t a = (p & ~uintptr_t(3)) + 4u * wd;
+              sh[b] = (int)(p & 3) * 8;
+              if (wd <= wpr && a < img_end) lo[b] = __ldg(reinterpret_cast<const uint32_t*>(a));
+              if (lane == 31 && sh[b] != 0 && a + 4 < img_end) nx[b] = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < kRowsInFlight; ++b) {
+            const int sr = sr0 + b * kWarps;
+            const uint32_t up = __shfl_down_sync(0xffffffffu, lo[b], 1);
+            const uint32_t hi = lane == 31 ? nx[b] : up;
+            if (sr < nrows && wd < wpr) sw[sr * wpr + wd] = __funnelshift_r(lo[b], hi, sh[b]);  // byte k = byte k of the image row
+          }
+        }
+      }
+    }
     if (j.hb) {
       int32_t* kcoef = reinterpret_cast<int32_t*>(smem + coef_off);  // [hk][tw] transposed: conflict-free
       for (int i = threadIdx.x; i < j.hk * tw; i += kThreads) {
         const int t = i / tw, x = i % tw;
         kcoef[i] = j.hc[(size_t)(x0 + x) * j.hk + t];
       }
-      __syncthreads();
-      const int x = threadIdx.x;
-      if (x < tw) {
-        const int xmin = j.hb[2 * (x0 + x)], cnt = j.hb[2 * (x0 + x) + 1];
-        const int round0 = 1 << (j.hprec - 1);
-        for (int rb = 0; rb < rows_in; rb += kRB) {
+    }
+    __syncthreads();
+
+    // ---- phase 1: horizontal pass (or plain copy) stage -> mid. One thread per output column: its tap window and
+    // coefficients are read once and reused for every row and channel (kRB rows of accumulators in registers).
+    {
+      const int groups = kThreads / tw;  // thread = (output column, row-block group): keeps all lanes busy at any tile width
+      const int x = threadIdx.x % tw, grp = threadIdx.x / tw;
+      const int chan_in_row = j.layout == KOCR_LAYOUT_HWC ? 1 : 0;  // byte step between channels inside a staged row
+      const uint32_t stage_u32 = smem_u32(stage);
+      if (grp < groups) {
+        int xmin = x0 + x, cnt = 1;
+        if (j.hb) { xmin = j.hb[2 * (x0 + x)]; cnt = j.hb[2 * (x0 + x) + 1]; }
+        const int32_t* kcoef = reinterpret_cast<const int32_t*>(smem + coef_off);
+        const int round0 = j.hb ? 1 << (j.hprec - 1) : 0;
+        const int shr = j.hb ? j.hprec : 0;
+        const int col_off = (xmin - xin0) * j.pix_stride;
+        for (int rb = grp * kRB; rb < rows_in; rb += kRB * groups) {
           int acc[3][kRB];
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int r = 0; r < kRB; ++r) acc[c][r] = round0;
-          const uint8_t* col = j.src + (long long)(r0 + rb) * j.row_pitch + (long long)xmin * j.pix_stride;
           const int nr = min(kRB, rows_in - rb);
-          for (int t = 0; t < cnt; ++t, col += j.pix_stride) {
-            const int kt = kcoef[t * tw + x];
+          // rows past the strip's last input row read padding of the staging buffer; their sums are discarded below
+          for (int t = 0; t < cnt; ++t) {
+            const int kt = j.hb ? kcoef[t * tw + x] : 1;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const uint8_t* pc = col + c * j.chan_stride;
+              const int sg = nseg == 3 ? c : 0;
+              uint32_t a = stage_u32 + (uint32_t)((sg * rows_in + rb) * Lp + col_off + t * j.pix_stride + c * chan_in_row);
 #pragma unroll
-              for (int r = 0; r < kRB; ++r, pc += j.row_pitch)
-                if (r < nr) acc[c][r] += (int)__ldg(pc) * kt;
+              for (int r = 0; r < kRB; ++r, a += Lp) acc[c][r] += (int)lds_u8(a) * kt;
             }
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int r = 0; r < kRB; ++r)
-              if (rb + r < rows_in) mid[((size_t)c * rows_in + rb + r) * tw + x] = (uint8_t)min(max(acc[c][r] >> j.hprec, 0), 255);
+              if (r < nr) mid[((size_t)c * rows_in + rb + r) * tw + x] = (uint8_t)min(max(acc[c][r] >> shr, 0), 255);
         }
-      }
-    } else {
-      const int n1 = 3 * rows_in * tw;
-      for (int i = threadIdx.x; i < n1; i += kThreads) {
-        const int x = i % tw;
-        const int rc = i / tw;
-        mid[i] = load_px(j, rc / rows_in, r0 + rc % rows_in, x0 + x);
       }
     }
     __syncthreads();
@@ -143,32 +215,42 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
       __syncthreads();
     }
 
-    // ---- phase 3: normalise + patch-order write. unit = 2 px of one (token, c, py) run, written for tp = 0 and 1.
+    // ---- phase 3: normalise + patch order, staged in smem. One thread per (token, channel, patch row) run of 14 px:
+    // 7 two-byte loads, 14 LUT reads, the run written for both temporal copies. The tile's tokens are ONE contiguous
+    // span of pixel_values, so the whole staged tile leaves with a single bulk async copy (no LSU store traffic).
     const int cells = tw / kStrip;
     const int gw2 = j.out_w / kStrip;  // merge cells per row
     const long long n0 = j.token_base + ((long long)sy * gw2 + x0 / kStrip) * 4;
-    const int units = cells * 4 * 294;
-    for (int u = threadIdx.x; u < units; u += kThreads) {
-      const int t = u / 294, r = u % 294;
-      const int c = r / 98, r2 = r % 98;
-      const int py = r2 / 7, jx = r2 % 7;
+    constexpr int kElt = kBf16 ? 2 : 4;
+    uint8_t* obuf = smem + out_off;  // the staged input it aliased was consumed in phase 1 (two barriers ago)
+    const int runs = cells * 4 * 42;
+    for (int run = threadIdx.x; run < runs; run += kThreads) {
+      const int t = run / 42, rr = run % 42;
+      const int c = rr / 14, py = rr % 14;
       const int cell = t >> 2, mh = (t >> 1) & 1, mw = t & 1;
-      const int y = mh * 14 + py, x = cell * kStrip + mw * 14 + 2 * jx;
-      const uint8_t* p = res + ((size_t)c * kStrip + y) * tw + x;
-      const float v0 = lut[c * 256 + p[0]], v1 = lut[c * 256 + p[1]];
-      const long long e = (n0 + t) * kPatchDim + c * 392 + py * 14 + 2 * jx;
-      if (kBf16) {
-        uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + e);
-        const uint32_t pk = pack_bf16(v0, v1);
-        o[0] = pk;
-        o[98] = pk;  // tp = 1 copy, 196 elements further
-      } else {
-        float2* o = reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + e);
-        o[0] = make_float2(v0, v1);
-        o[98] = make_float2(v0, v1);
+      const uint16_t* p = reinterpret_cast<const uint16_t*>(res + ((size_t)c * kStrip + mh * 14 + py) * tw + cell * kStrip + mw * 14);
+      uint8_t* d = obuf + ((size_t)t * kPatchDim + c * 392 + py * 14) * kElt;
+      const float* l = lut + c * 256;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const uint32_t u = p[k];
+        const float v0 = l[u & 255], v1 = l[u >> 8];
+        if (kBf16) {
+          const uint32_t pk = pack_bf16(v0, v1);
+          reinterpret_cast<uint32_t*>(d)[k] = pk;
+          reinterpret_cast<uint32_t*>(d + 196 * kElt)[k] = pk;  // tp = 1 copy
+        } else {
+          reinterpret_cast<float2*>(d)[k] = make_float2(v0, v1);
+          reinterpret_cast<float2*>(d + 196 * kElt)[k] = make_float2(v0, v1);
+        }
       }
     }
+    fence_proxy_async();  // make the generic-proxy smem writes visible to the bulk copy engine
+    __syncthreads();
+    if (threadIdx.x == 0)
+      bulk_store(reinterpret_cast<uint8_t*>(out) + n0 * kPatchDim * kElt, obuf, (uint32_t)(cells * 4 * kPatchDim * kElt));
   }
+  if (threadIdx.x == 0) bulk_store_wait_all();
 }
 
 struct AxisTable {
@@ -218,8 +300,8 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     return fail(KOCR_ERR_INVALID, "kocr_preprocess: bad resize_mode");
   if (out_dtype != KOCR_DTYPE_F32 && out_dtype != KOCR_DTYPE_BF16)
     return fail(KOCR_ERR_INVALID, "kocr_preprocess: out_dtype must be F32 or BF16");
-  if ((reinterpret_cast<uintptr_t>(pixel_values) & 7) != 0)
-    return fail(KOCR_ERR_INVALID, "kocr_preprocess: pixel_values must be 8-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(pixel_values) & 15) != 0)
+    return fail(KOCR_ERR_INVALID, "kocr_preprocess: pixel_values must be 16-byte aligned");
 
   // ---- plan on the host: sizes, filter banks (deduplicated), tiles
   if (table_cache().size() > 256) table_cache().clear();  // bound the per-thread cache (pointers below stay valid)
@@ -238,7 +320,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   std::vector<const AxisTable*> ht(n_images, nullptr), vt(n_images, nullptr);
   int64_t tokens = 0;
   int tiles = 0, max_mid = 0, max_res = 0;
-  const int kSmemBudget = 96 * 1024;
+  const int kSmemBudget = 64 * 1024;
   for (int i = 0; i < n_images; ++i) {
     const KocrImage& im = images[i];
     if (!im.data || im.layout < 0 || im.layout > 2) return fail(KOCR_ERR_INVALID, "kocr_preprocess: bad image");
@@ -251,13 +333,14 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     memset(&j, 0, sizeof j);
     j.src = im.data;
     j.in_h = im.height; j.in_w = im.width; j.layout = im.layout;
+    j.src_bytes = (long long)im.height * im.width * (im.layout == KOCR_LAYOUT_GRAY ? 1 : 3);
     if (im.layout == KOCR_LAYOUT_CHW) { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = (long long)im.height * im.width; }
     else if (im.layout == KOCR_LAYOUT_HWC) { j.pix_stride = 3; j.row_pitch = 3 * im.width; j.chan_stride = 1; }
     else { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = 0; }
     j.out_h = oh; j.out_w = ow;
     j.token_base = tokens;
     const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
-    int tw = 252;
+    int tw = 112;  // staged output tile: 16 tokens = 37.6 KB (bf16) / 75.3 KB (f32); keeps 3+ CTAs resident per SM
     while (tw > kStrip && 3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > kSmemBudget) tw -= kStrip;
     if (3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > 200 * 1024)
       return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: vertical downscale factor too large for one tile");
@@ -311,19 +394,33 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   int max_coef = 0;
   for (int i = 0; i < n_images; ++i)
     if (ht[i]) max_coef = std::max(max_coef, ht[i]->ksize * jobs[i].tile_w * 4);
+  int max_tw = 0;
+  for (int i = 0; i < n_images; ++i) max_tw = std::max(max_tw, jobs[i].tile_w);
   const int coef_off = (max_mid + max_res + 15) & ~15;
-  const int smem = coef_off + max_coef;
+  const int out_off = (coef_off + max_coef + 127) & ~127;
+  int stage_bytes = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const PageJob& j = jobs[i];
+    const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
+    const double scale = std::max(1.0, (double)j.in_w / j.out_w);
+    const int ncols = (int)(j.tile_w * scale) + 2 * (ht[i] ? ht[i]->ksize : 0) + 8;  // generous bound on the tap span
+    const int lp = ((ncols * j.pix_stride + 6) & ~3) + 4;
+    stage_bytes = std::max(stage_bytes, ((j.layout == KOCR_LAYOUT_CHW ? 3 : 1) * rows_in + kRB) * lp);  // + padding rows
+  }
+  const int out_bytes = (max_tw / kStrip) * 4 * kPatchDim * (out_dtype == KOCR_DTYPE_BF16 ? 2 : 4);
+  const int smem = out_off + std::max(out_bytes, stage_bytes);
+  if (smem > 220 * 1024) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: tile does not fit in shared memory");
   const int grid = std::min(tiles, ctx->num_sms * 8);
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
   ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
     KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                              pixel_values, max_mid, coef_off);
+                                                              pixel_values, max_mid, coef_off, out_off);
   } else {
     KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                               pixel_values, max_mid, coef_off);
+                                                               pixel_values, max_mid, coef_off, out_off);
   }
   KOCR_LAUNCH_CHECK("preprocess_kernel");
   return KOCR_OK;
