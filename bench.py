@@ -273,10 +273,16 @@ def run_gpu(args):
         for k, v in per_class.items():
             if k in flops_by_class:
                 v["tflops"] = flops_by_class[k] / (v["ms_per_launch"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp) and n_pages == PAGES_PER_STEP:  # ncu dram__bytes_read+write per launch at this batch size
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["dram_bytes_per_launch"].get(dom), tj["source"]
         if dom in flops_by_class:
             achieved = flops_by_class[dom] / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                        "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "flops_per_launch": flops_by_class[dom]}
         else:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}

@@ -103,9 +103,12 @@ __device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
   return pack_u32x2(b0, b1);
 }
 
+// kWin: block-diagonal attention inside a query block (Qwen2.5-VL windows, HF modeling_qwen2_5_vl.py:498-502): row r may
+// attend only the keys [win[r].x, win[r].y) of its own window; a 256-row block packs four or more windows.
+template <bool kWin>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                 const AttnWork* __restrict__ work, int num_heads) {
+                 const AttnWork* __restrict__ work, int num_heads, const int2* __restrict__ win) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                                   // 2 tiles
@@ -253,6 +256,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
     const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
     float m_ref = -INFINITY, l = 0.f;
+    int w_lo = 0, w_hi = 0;  // this row's window, as key indices relative to kv_begin
+    if (kWin) {
+      const int qr = t * kTileRows + r;
+      if (qr < w.q_rows) {
+        const int2 wb = win[w.q_begin + qr];
+        w_lo = wb.x - w.kv_begin;
+        w_hi = wb.y - w.kv_begin;
+      }
+    }
 #if KOCR_PREFETCH_S
     uint32_t sr[kSub];
     mbar_wait(&s_full[t * 2], 0);
@@ -272,11 +284,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       tmem_ld_x32(t_s + 32, sr + 32);
       tc_wait_ld();
 #endif
-      const int valid = w.kv_len - i * kSub;
-      if (valid < kSub) {
+      if (kWin) {
+        const int c_lo = w_lo - i * kSub, c_hi = w_hi - i * kSub;  // valid columns of this sub-step: [c_lo, c_hi)
+        if (c_lo > 0 || c_hi < kSub) {
 #pragma unroll
-        for (int c = 0; c < kSub; ++c)
-          if (c >= valid) sr[c] = 0xff800000u;  // -inf
+          for (int c = 0; c < kSub; ++c)
+            if (c < c_lo || c >= c_hi) sr[c] = 0xff800000u;  // -inf
+        }
+      } else {
+        const int valid = w.kv_len - i * kSub;
+        if (valid < kSub) {
+#pragma unroll
+          for (int c = 0; c < kSub; ++c)
+            if (c >= valid) sr[c] = 0xff800000u;  // -inf
+        }
       }
       // row max: 4 independent FMNMX3 chains
       float mxa[4];
@@ -295,7 +316,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         m_ref = mx;
       }
       // p = 2^(s - m): packed f32x2 subtract and 4 independent packed row-sum accumulators
-      const uint64_t neg_m2 = pack_f32x2(-m_ref, -m_ref);
+      // (a row whose keys so far are all masked still has m_ref = -inf: subtract 0 so its p are 2^-inf = 0, not NaN)
+      const float neg_m = (kWin && m_ref == -INFINITY) ? 0.f : -m_ref;
+      const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[kSub / 2];
 #pragma unroll
@@ -390,7 +413,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
 }
 
 int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_work, int n_work, int num_heads,
-                     int64_t total_rows, cudaStream_t stream) {
+                     int64_t total_rows, cudaStream_t stream, const int2* d_win) {
   if (n_work <= 0) return KOCR_OK;
   if (num_heads <= 0 || num_heads > 65535) return fail(KOCR_ERR_UNSUPPORTED, "attention: bad head count");
   CUtensorMap tm;
@@ -401,11 +424,15 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   if (rc) return rc;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
   dim3 grid((unsigned)n_work, (unsigned)num_heads);
-  attention_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<__nv_bfloat16*>(out), d_work, num_heads);
+  if (d_win)
+    attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
+  else
+    attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
   KOCR_LAUNCH_CHECK("attention_kernel");
   return KOCR_OK;
 }
@@ -417,6 +444,31 @@ int build_attn_work(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out) {
     const int b = cu[i], len = cu[i + 1] - cu[i];
     if (len <= 0) return fail(KOCR_ERR_INVALID, "attention: empty or negative sequence");
     for (int q = 0; q < len; q += 2 * kTileRows) out->push_back(AttnWork{b + q, std::min(2 * kTileRows, len - q), b, len});
+  }
+  return KOCR_OK;
+}
+
+// Host: windowed layers. Sequences are whole images (cu), windows are the contiguous segments cu_win inside them;
+// query blocks of 256 rows per image, each with the key range spanned by its rows' windows, plus the per-row table.
+int build_attn_work_windowed(const int32_t* cu, int n_seqs, const int32_t* cu_win, int n_win, std::vector<AttnWork>* out,
+                             std::vector<int32_t>* row_win) {
+  out->clear();
+  const int total = cu[n_seqs];
+  row_win->assign((size_t)total * 2, 0);
+  for (int k = 0; k < n_win; ++k) {
+    if (cu_win[k + 1] <= cu_win[k] || cu_win[k + 1] > total) return fail(KOCR_ERR_INVALID, "attention: bad window table");
+    for (int r = cu_win[k]; r < cu_win[k + 1]; ++r) {
+      (*row_win)[2 * (size_t)r] = cu_win[k];
+      (*row_win)[2 * (size_t)r + 1] = cu_win[k + 1];
+    }
+  }
+  for (int i = 0; i < n_seqs; ++i) {
+    const int b = cu[i], e = cu[i + 1];
+    for (int q = b; q < e; q += 2 * kTileRows) {
+      const int rows = std::min(2 * kTileRows, e - q);
+      const int kv0 = (*row_win)[2 * (size_t)q], kv1 = (*row_win)[2 * (size_t)(q + rows - 1) + 1];
+      out->push_back(AttnWork{q, rows, kv0, kv1 - kv0});
+    }
   }
   return KOCR_OK;
 }
@@ -439,5 +491,5 @@ extern "C" int kocr_op_attention(KocrCtx* ctx_, const void* qkv, void* out, cons
   rc = ctx->stage(work.data(), work.size() * sizeof(AttnWork), stream, &d_work);
   if (rc) return rc;
   return launch_attention(ctx, qkv, out, static_cast<const AttnWork*>(d_work), (int)work.size(), num_heads,
-                          cu_seqlens_host[n_seqs], stream);
+                          cu_seqlens_host[n_seqs], stream, nullptr);
 }

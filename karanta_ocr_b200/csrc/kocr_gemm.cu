@@ -226,10 +226,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             hi[i] = (x2 * t.x + x1 * t.y) * mul;
           }
           if (row_ok) {
-            *reinterpret_cast<uint4*>(orow + c_qk + c * 8) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
-                                                                        pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-            *reinterpret_cast<uint4*>(orow + c_qk + 40 + c * 8) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]),
-                                                                             pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+            // q and k are stored with their head dims permuted to [j0..7, j40..47, j8..15, j48..55, ...]: q.k is invariant
+            // under a permutation applied to both, and each iteration becomes one aligned 256-bit store
+            const uint32_t w8[8] = {pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]),
+                                    pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7])};
+            stg_256(orow + c_qk + c * 16, w8);
           }
         }
         // v share: 40 columns = 5 x8 loads; the first two are already in flight in a[1], b[1] (5 & 1 == 1)
@@ -246,14 +247,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         }
         tc_wait_ld();
         if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c_v);
           const uint32_t* src[5] = {a[1], b[1], v2[0], v2[1], v2[2]};
+          uint32_t w[20];
 #pragma unroll
-          for (int g = 0; g < 5; ++g) {
-            float o[8];
+          for (int g = 0; g < 5; ++g)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(src[g][i]) + vb[g * 8 + i];
-            dst[g] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            for (int i = 0; i < 4; ++i)
+              w[g * 4 + i] = pack_bf16(__uint_as_float(src[g][2 * i]) + vb[g * 8 + 2 * i],
+                                       __uint_as_float(src[g][2 * i + 1]) + vb[g * 8 + 2 * i + 1]);
+          // v keeps its natural order. Its 80-byte share starts 32-byte aligned for half 0 and 16 bytes off for half 1.
+          __nv_bfloat16* dst = orow + c_v;
+          if (half == 0) {
+            stg_256(dst, w);
+            stg_256(dst + 16, w + 8);
+            *reinterpret_cast<uint4*>(dst + 32) = make_uint4(w[16], w[17], w[18], w[19]);
+          } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            stg_256(dst + 8, w + 4);
+            stg_256(dst + 24, w + 12);
           }
         }
       } else {
@@ -380,7 +391,7 @@ int launch_gemm(Ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb
     return fail(KOCR_ERR_UNSUPPORTED, "gemm: C and residual must be 32-byte aligned (256-bit epilogue accesses)");
   const int bn = (epi == kEpiQkvRope) ? 240 : 256;
   if (epi == kEpiQkvRope) {
-    if (N % 240) return fail(KOCR_ERR_UNSUPPORTED, "gemm(qkv_rope): N must be a multiple of 240");
+    if (N % 240 || ep.ldc % 16) return fail(KOCR_ERR_UNSUPPORTED, "gemm(qkv_rope): N must be a multiple of 240, ldc of 16");
   } else if (epi == KOCR_EPI_BIAS_SWIGLU) {
     if (N % 64) return fail(KOCR_ERR_UNSUPPORTED, "gemm(swiglu): N must be a multiple of 64");
   } else if (N % 32) {

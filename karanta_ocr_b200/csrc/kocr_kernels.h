@@ -40,7 +40,8 @@ int launch_gather_groups(const void* src, void* dst, const int32_t* index, int64
 
 // varlen attention over the tower's QKV layout [S, heads, 3, 80]; seq table on device
 struct AttnWork { int q_begin; int q_rows; int kv_begin; int kv_len; };  // one CTA work item (a 256-row q block of one sequence)
+// d_win != nullptr: windowed mode, d_win[row] = (first key row, one past the last key row) of the row's window
 int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_work, int n_work, int num_heads,
-                     int64_t total_rows, cudaStream_t stream);
+                     int64_t total_rows, cudaStream_t stream, const int2* d_win = nullptr);
 
 }  // namespace kocr

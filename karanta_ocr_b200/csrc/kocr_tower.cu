@@ -16,6 +16,8 @@
 namespace kocr {
 
 int build_attn_work(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out);
+int build_attn_work_windowed(const int32_t* cu, int n_seqs, const int32_t* cu_win, int n_win, std::vector<AttnWork>* out,
+                             std::vector<int32_t>* row_win);
 
 struct BlockW {
   float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
@@ -357,14 +359,16 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   }
   std::vector<AttnWork> work_full, work_win;
   if ((rc = build_attn_work(cu.data(), n_cu - 1, &work_full))) return rc;
-  if (t->q25 && (rc = build_attn_work(cuw.data(), n_cuw - 1, &work_win))) return rc;
+  std::vector<int32_t> row_win;
+  if (t->q25 && (rc = build_attn_work_windowed(cu.data(), n_cu - 1, cuw.data(), n_cuw - 1, &work_win, &row_win))) return rc;
 
   // ---- stage the tables
   const size_t off_pos = 0;
   const size_t off_wf = align256(pos.size() * 4);
   const size_t off_ww = off_wf + align256(work_full.size() * sizeof(AttnWork));
   const size_t off_wi = off_ww + align256(work_win.size() * sizeof(AttnWork));
-  const size_t total = off_wi + align256(widx.size() * 4);
+  const size_t off_rw = off_wi + align256(widx.size() * 4);
+  const size_t total = off_rw + align256(row_win.size() * 4);
   void* hs;
   int slot;
   if ((rc = ctx->stage_begin(total, &hs, &slot))) return rc;
@@ -373,6 +377,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   memcpy(hb + off_wf, work_full.data(), work_full.size() * sizeof(AttnWork));
   if (!work_win.empty()) memcpy(hb + off_ww, work_win.data(), work_win.size() * sizeof(AttnWork));
   if (!widx.empty()) memcpy(hb + off_wi, widx.data(), widx.size() * 4);
+  if (!row_win.empty()) memcpy(hb + off_rw, row_win.data(), row_win.size() * 4);
   void* ds;
   if ((rc = ctx->stage_commit(slot, total, st, &ds))) return rc;
   uint8_t* db = static_cast<uint8_t*>(ds);
@@ -380,6 +385,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   const AttnWork* d_wf = reinterpret_cast<const AttnWork*>(db + off_wf);
   const AttnWork* d_ww = reinterpret_cast<const AttnWork*>(db + off_ww);
   const int32_t* d_wi = reinterpret_cast<const int32_t*>(db + off_wi);
+  const int2* d_rw = reinterpret_cast<const int2*>(db + off_rw);
 
   // ---- patch embed (HF :304-310; Conv3d with kernel == stride is a GEMM over the flattened patch)
   const void* pv = pixel_values;
@@ -423,7 +429,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
     {
       ProfScope ps(ctx, kProfAttention, st);
       if (full) rc = launch_attention(ctx, qkv, attn, d_wf, (int)work_full.size(), H, S, st);
-      else rc = launch_attention(ctx, qkv, attn, d_ww, (int)work_win.size(), H, S, st);
+      else rc = launch_attention(ctx, qkv, attn, d_ww, (int)work_win.size(), H, S, st, d_rw);
       if (rc) return rc;
     }
     GemmEpilogue e2{};
