@@ -190,6 +190,41 @@ int launch_permute_rows(const void* src, void* dst, const int32_t* perm, int64_t
   return KOCR_OK;
 }
 
+// ---------------------------------------------------------------- LayerNorm folding into the following Linear (prepack)
+__global__ void __launch_bounds__(256) fold_norm_kernel(__nv_bfloat16* __restrict__ W, int64_t ldw, float* __restrict__ bias,
+                                                        float* __restrict__ c1, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t N, int64_t K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  __nv_bfloat16* w = W + n * ldw;
+  float acc_b = 0.f, acc_c = 0.f;
+  for (int64_t k = lane; k < K; k += 32) {
+    const float v = __bfloat162float(w[k]);
+    if (beta) acc_b += beta[k] * v;
+    const __nv_bfloat16 s = __float2bfloat16_rn(v * gamma[k]);
+    acc_c += __bfloat162float(s);
+    w[k] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_b += __shfl_xor_sync(0xffffffffu, acc_b, o);
+    acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+  }
+  if (lane == 0) {
+    bias[n] += acc_b;
+    c1[n] = acc_c;
+  }
+}
+
+int launch_fold_norm(void* W, int64_t ldw, float* bias, float* c1, const float* gamma, const float* beta, int64_t N, int64_t K,
+                     cudaStream_t stream) {
+  if (N <= 0) return KOCR_OK;
+  fold_norm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(W), ldw, bias, c1, gamma, beta, N, K);
+  KOCR_LAUNCH_CHECK("fold_norm_kernel");
+  return KOCR_OK;
+}
+
 // ---------------------------------------------------------------- RoPE table
 __global__ void rope_table_kernel(float2* cs, int max_pos, int n_freq, float theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -172,6 +172,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + acc * S::kAccStride + ((uint32_t)(q * 32) << 16);
+      // folded LayerNorm / RMSNorm: mean and 1/std of this thread's row of A from the producer's partial sums
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      const bool ln_on = ep.ln_part != nullptr;
+      if (ln_on && row_ok) {
+        float s1 = 0.f, s2 = 0.f;
+        const float2* pp = ep.ln_part + (size_t)row * ep.ln_slots;
+        for (int i = 0; i < ep.ln_slots; ++i) {
+          const float2 v = pp[i];
+          s1 += v.x;
+          s2 += v.y;
+        }
+        if (ep.ln_rms) {
+          ln_rstd = rsqrtf(s2 * ep.ln_inv_dim + ep.ln_eps);
+        } else {
+          ln_mean = s1 * ep.ln_inv_dim;
+          ln_rstd = rsqrtf(fmaxf(s2 * ep.ln_inv_dim - ln_mean * ln_mean, 0.f) + ep.ln_eps);
+        }
+      }
 
       if constexpr (EPI == kEpiQkvRope) {
         // BN == 240 = [q_h | k_h | v_h] of one head (weights prepacked in that order).
@@ -216,11 +234,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           const float4 b2b = __ldg(reinterpret_cast<const float4*>(brow + c_qk + 40 + c * 8 + 4));
           const float bb1[8] = {b1a.x, b1a.y, b1a.z, b1a.w, b1b.x, b1b.y, b1b.z, b1b.w};
           const float bb2[8] = {b2a.x, b2a.y, b2a.z, b2a.w, b2b.x, b2b.y, b2b.z, b2b.w};
+          float cc1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cc2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (ln_on && !ep.ln_rms) {
+            const float* crow = ep.ln_c1 + n0 + c_qk + c * 8;
+            const float4 c1a = __ldg(reinterpret_cast<const float4*>(crow)), c1b = __ldg(reinterpret_cast<const float4*>(crow + 4));
+            const float4 c2a = __ldg(reinterpret_cast<const float4*>(crow + 40)), c2b = __ldg(reinterpret_cast<const float4*>(crow + 44));
+            cc1[0] = c1a.x; cc1[1] = c1a.y; cc1[2] = c1a.z; cc1[3] = c1a.w; cc1[4] = c1b.x; cc1[5] = c1b.y; cc1[6] = c1b.z; cc1[7] = c1b.w;
+            cc2[0] = c2a.x; cc2[1] = c2a.y; cc2[2] = c2a.z; cc2[3] = c2a.w; cc2[4] = c2b.x; cc2[5] = c2b.y; cc2[6] = c2b.z; cc2[7] = c2b.w;
+          }
           float lo[8], hi[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float x1 = __uint_as_float(a[c & 1][i]) + bb1[i];
-            const float x2 = __uint_as_float(b[c & 1][i]) + bb2[i];
+            const float x1 = ln_rstd * (__uint_as_float(a[c & 1][i]) - ln_mean * cc1[i]) + bb1[i];
+            const float x2 = ln_rstd * (__uint_as_float(b[c & 1][i]) - ln_mean * cc2[i]) + bb2[i];
             const float2 t = cs[c * 8 + i];
             lo[i] = (x1 * t.x - x2 * t.y) * mul;
             hi[i] = (x2 * t.x + x1 * t.y) * mul;
@@ -239,11 +265,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         tmem_ld_x8(t_row + c_v + 16, v2[0]);
         tmem_ld_x8(t_row + c_v + 24, v2[1]);
         tmem_ld_x8(t_row + c_v + 32, v2[2]);
-        float vb[40];
+        float vb[40], vc[40];
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(brow + c_v) + i);
           vb[4 * i] = t.x; vb[4 * i + 1] = t.y; vb[4 * i + 2] = t.z; vb[4 * i + 3] = t.w;
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ln_on && !ep.ln_rms) u = __ldg(reinterpret_cast<const float4*>(ep.ln_c1 + n0 + c_v) + i);
+          vc[4 * i] = u.x; vc[4 * i + 1] = u.y; vc[4 * i + 2] = u.z; vc[4 * i + 3] = u.w;
         }
         tc_wait_ld();
         if (row_ok) {
@@ -253,8 +282,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           for (int g = 0; g < 5; ++g)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              w[g * 4 + i] = pack_bf16(__uint_as_float(src[g][2 * i]) + vb[g * 8 + 2 * i],
-                                       __uint_as_float(src[g][2 * i + 1]) + vb[g * 8 + 2 * i + 1]);
+              w[g * 4 + i] = pack_bf16(ln_rstd * (__uint_as_float(src[g][2 * i]) - ln_mean * vc[g * 8 + 2 * i]) + vb[g * 8 + 2 * i],
+                                       ln_rstd * (__uint_as_float(src[g][2 * i + 1]) - ln_mean * vc[g * 8 + 2 * i + 1]) + vb[g * 8 + 2 * i + 1]);
           // v keeps its natural order. Its 80-byte share starts 32-byte aligned for half 0 and 16 bytes off for half 1.
           __nv_bfloat16* dst = orow + c_v;
           if (half == 0) {
@@ -285,15 +314,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
         uint32_t r[2][32];
+        float st_sum = 0.f, st_sq = 0.f;
         tmem_ld_x32(t_row + half * (BN / 2), r[0]);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           // bias of this chunk is fetched before the TMEM wait so both latencies overlap
-          float4 bv[8];
+          float4 bv[8], cv[8];
           if constexpr (EPI != KOCR_EPI_NONE) {
             if (c < nch) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c * 32) + i);
+              if (ln_on && !ep.ln_rms) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cv[i] = __ldg(reinterpret_cast<const float4*>(ep.ln_c1 + col0 + c * 32) + i);
+              }
             }
           }
           tc_wait_ld();
@@ -309,10 +343,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if constexpr (EPI == KOCR_EPI_NONE) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              v[4 * i] = __uint_as_float(r[c & 1][4 * i]) + bv[i].x;
-              v[4 * i + 1] = __uint_as_float(r[c & 1][4 * i + 1]) + bv[i].y;
-              v[4 * i + 2] = __uint_as_float(r[c & 1][4 * i + 2]) + bv[i].z;
-              v[4 * i + 3] = __uint_as_float(r[c & 1][4 * i + 3]) + bv[i].w;
+              if (!(ln_on && !ep.ln_rms)) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * i] = ln_rstd * (__uint_as_float(r[c & 1][4 * i]) - ln_mean * cv[i].x) + bv[i].x;
+              v[4 * i + 1] = ln_rstd * (__uint_as_float(r[c & 1][4 * i + 1]) - ln_mean * cv[i].y) + bv[i].y;
+              v[4 * i + 2] = ln_rstd * (__uint_as_float(r[c & 1][4 * i + 2]) - ln_mean * cv[i].z) + bv[i].z;
+              v[4 * i + 3] = ln_rstd * (__uint_as_float(r[c & 1][4 * i + 3]) - ln_mean * cv[i].w) + bv[i].w;
             }
             if constexpr (EPI == KOCR_EPI_BIAS_QUICKGELU) {
 #pragma unroll
@@ -342,9 +377,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 stg_256(orow + c * 16, w8);
               }
             } else {
-              if (row_ok) store_bf16x32(orow + c * 32, v);
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+              if (ep.stat_part) {  // statistics of the values as the next norm will read them (bf16-rounded)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float x0 = bf16_lo(w[i]), x1 = bf16_hi(w[i]);
+                  st_sum += x0 + x1;
+                  st_sq += x0 * x0 + x1 * x1;
+                }
+              }
+              if (row_ok) {
+                stg_256(orow + c * 32, w);
+                stg_256(orow + c * 32 + 16, w + 8);
+              }
             }
           }
+        }
+        if constexpr (EPI == KOCR_EPI_BIAS_RESIDUAL || EPI == KOCR_EPI_NONE) {
+          if (ep.stat_part && row_ok) ep.stat_part[(size_t)row * ep.stat_slots + (tile % num_n) * 2 + half] = make_float2(st_sum, st_sq);
         }
       }
       // all of this warp's TMEM reads are complete (wait::ld above): hand the accumulator stage back

@@ -23,6 +23,7 @@ struct BlockW {
   float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
   __nv_bfloat16 *w_qkv = nullptr, *w_proj = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;  // fc1 = gate|up interleaved, fc2 = down (2.5)
   float *b_qkv = nullptr, *b_proj = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+  float *c1_qkv = nullptr, *c1_fc1 = nullptr;  // row sums of the gamma-scaled weights (norm1 -> qkv, norm2 -> fc1 folding)
 };
 
 struct Tower {
@@ -40,6 +41,8 @@ struct Tower {
   int32_t* d_qkv_perm = nullptr;
   int32_t* d_gu_perm = nullptr;
   std::set<std::string> loaded;
+  bool folded = false;  // norm1/norm2 have been folded into the qkv / fc1 weights (kocr_tower_finalize)
+  int stat_slots = 0;   // partial-statistics slots per row = 2 * ceil(D / 256)
   std::vector<void*> allocs;
 
   template <typename T>
@@ -87,7 +90,7 @@ static int64_t numel(const int64_t* shape, int ndim) {
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct WsLayout {
-  size_t pv = 0, x = 0, xn = 0, qkv = 0, attn = 0, h = 0, x2 = 0, total = 0;
+  size_t pv = 0, x = 0, xn = 0, qkv = 0, attn = 0, h = 0, x2 = 0, st_a = 0, st_b = 0, st_tmp = 0, total = 0;
 };
 
 static WsLayout ws_layout(const Tower& t, int64_t S, bool need_pv) {
@@ -101,6 +104,9 @@ static WsLayout ws_layout(const Tower& t, int64_t S, bool need_pv) {
   w.attn = take((size_t)S * t.D * 2);
   w.h = take((size_t)S * std::max(t.Fp, t.O) * 2);
   w.x2 = take(t.q25 ? (size_t)S * t.D * 2 : 0);
+  w.st_a = take((size_t)S * t.stat_slots * sizeof(float2));
+  w.st_b = take((size_t)S * t.stat_slots * sizeof(float2));
+  w.st_tmp = take(t.q25 ? (size_t)S * t.stat_slots * sizeof(float2) : 0);
   w.total = o + 256;
   return w;
 }
@@ -133,6 +139,7 @@ int kocr_tower_create(KocrCtx* ctx_, const KocrTowerConfig* cfg, KocrTower** out
   t->Fp = (cfg->mlp_hidden + 31) / 32 * 32;
   t->O = cfg->out_hidden;
   t->PD = cfg->in_channels * cfg->temporal_patch_size * cfg->patch_size * cfg->patch_size;
+  t->stat_slots = 2 * ((cfg->embed_dim + 255) / 256);
   if (t->PD % 8) { delete t; return fail(KOCR_ERR_UNSUPPORTED, "patch dim must be a multiple of 8"); }
   const int D = t->D, Fp = t->Fp, O = t->O;
   int rc = t->alloc(&t->w_patch, (size_t)D * t->PD);
@@ -141,7 +148,8 @@ int kocr_tower_create(KocrCtx* ctx_, const KocrTowerConfig* cfg, KocrTower** out
     BlockW& b = t->blk[i];
     rc = t->alloc(&b.n1w, D) || t->alloc(&b.n2w, D) || t->alloc(&b.n1b, D, true) || t->alloc(&b.n2b, D, true) ||
          t->alloc(&b.w_qkv, (size_t)3 * D * D) || t->alloc(&b.b_qkv, 3 * D) || t->alloc(&b.w_proj, (size_t)D * D) ||
-         t->alloc(&b.b_proj, D);
+         t->alloc(&b.b_proj, D) || t->alloc(&b.c1_qkv, 3 * D, true) ||
+         t->alloc(&b.c1_fc1, (size_t)(cfg->arch == KOCR_ARCH_QWEN2_5_VL ? 2 : 1) * ((cfg->mlp_hidden + 31) / 32 * 32), true);
     if (rc) break;
     if (!t->q25) {
       rc = t->alloc(&b.w_fc1, (size_t)Fp * D, true) || t->alloc(&b.b_fc1, Fp, true) ||
@@ -191,6 +199,7 @@ int kocr_tower_set_weight(KocrTower* tower, const char* name_, const void* data,
   if (!t || !name_ || !data || !shape || ndim <= 0) return fail(KOCR_ERR_INVALID, "kocr_tower_set_weight: null argument");
   if (dtype < KOCR_DTYPE_F32 || dtype > KOCR_DTYPE_F16) return fail(KOCR_ERR_INVALID, "kocr_tower_set_weight: bad dtype");
   KOCR_CUDA_CHECK(cudaSetDevice(t->ctx->device));
+  if (t->folded) return fail(KOCR_ERR_STATE, "kocr_tower_set_weight: weights were already finalized (norms folded); create a new tower");
   const std::string name(name_);
   const int64_t n = numel(shape, ndim);
   const int D = t->D, F = t->F, Fp = t->Fp, O = t->O;
@@ -286,6 +295,19 @@ int kocr_tower_finalize(KocrTower* tower) {
       if (n_missing++ < 8) missing += (missing.empty() ? "" : ", ") + k;
     }
   if (n_missing) return fail(KOCR_ERR_STATE, "missing " + std::to_string(n_missing) + " weights: " + missing);
+  if (!t->folded) {
+    // Fold norm1 into qkv and norm2 into fc1 (gate/up): W' = W diag(gamma), b' = b + W beta, c1 = row sums of W'.
+    // The GEMM then reads the raw residual stream and applies mean / rstd per row in its epilogue (no norm pass).
+    KOCR_CUDA_CHECK(cudaSetDevice(t->ctx->device));
+    const int D = t->D;
+    for (BlockW& b : t->blk) {
+      int rc = launch_fold_norm(b.w_qkv, D, b.b_qkv, b.c1_qkv, b.n1w, t->q25 ? nullptr : b.n1b, 3 * D, D, 0);
+      if (!rc) rc = launch_fold_norm(b.w_fc1, D, b.b_fc1, b.c1_fc1, b.n2w, t->q25 ? nullptr : b.n2b, (t->q25 ? 2 : 1) * (int64_t)t->Fp, D, 0);
+      if (rc) return rc;
+    }
+    KOCR_CUDA_CHECK(cudaStreamSynchronize(0));
+    t->folded = true;
+  }
   return KOCR_OK;
 }
 
@@ -332,6 +354,10 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   auto* attn = reinterpret_cast<__nv_bfloat16*>(ws + wl.attn);
   auto* hbuf = reinterpret_cast<__nv_bfloat16*>(ws + wl.h);
   auto* x2 = reinterpret_cast<__nv_bfloat16*>(ws + wl.x2);
+  auto* st_a = reinterpret_cast<float2*>(ws + wl.st_a);   // row statistics of x after the attention residual (-> norm2)
+  auto* st_b = reinterpret_cast<float2*>(ws + wl.st_b);   // row statistics of x after the MLP residual / patch embed (-> norm1)
+  auto* st_tmp = reinterpret_cast<float2*>(ws + wl.st_tmp);
+  const int slots = t->stat_slots;
 
   if (max_pos > t->rope_max_pos) {  // grow the (cos, sin) table; rare
     KOCR_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -398,6 +424,8 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   __nv_bfloat16* x_embed = t->q25 ? x2 : x;
   ep.out = x_embed;
   ep.ldc = D;
+  ep.stat_part = t->q25 ? st_tmp : st_b;
+  ep.stat_slots = slots;
   {
     ProfScope ps(ctx, kProfPatchEmbed, st);
     if ((rc = launch_gemm(ctx, pv, t->PD, t->w_patch, t->PD, S, D, t->PD, KOCR_EPI_NONE, ep, st))) return rc;
@@ -405,6 +433,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   if (t->q25) {  // window-major permutation of 4-patch groups (HF qwen2_5 :478-481)
     ProfScope ps(ctx, kProfOther, st);
     if ((rc = launch_gather_groups(x2, x, d_wi, S / 4, 4, D, false, st))) return rc;
+    if ((rc = launch_gather_groups(st_tmp, st_b, d_wi, S / 4, 4, slots * 4, false, st))) return rc;  // the rows' statistics move with them
   }
 
   const float q_scale = (float)((1.0 / sqrt(80.0)) * 1.4426950408889634);
@@ -415,16 +444,13 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
       full = false;
       for (int k = 0; k < t->cfg.n_fullatt; ++k) full |= t->cfg.fullatt_block_indexes[k] == i;
     }
-    // norm1 -> qkv (+bias, RoPE, q scale) -> attention -> proj (+bias, +residual)
-    {
-      ProfScope ps(ctx, kProfNorm, st);
-      if ((rc = launch_norm(x, D, b.n1w, t->q25 ? nullptr : b.n1b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
-    }
+    // [norm1 folded] qkv (+bias, RoPE, q scale) -> attention -> proj (+bias, +residual, row statistics for norm2)
     GemmEpilogue e1{};
     e1.bias = b.b_qkv; e1.out = qkv; e1.ldc = 3 * D; e1.pos_hw = d_pos; e1.rope_cs = t->rope_cs; e1.q_scale = q_scale;
+    e1.ln_part = st_b; e1.ln_c1 = b.c1_qkv; e1.ln_slots = slots; e1.ln_rms = t->q25; e1.ln_inv_dim = 1.0f / D; e1.ln_eps = 1e-6f;
     {
       ProfScope ps(ctx, kProfQkvRope, st);
-      if ((rc = launch_gemm(ctx, xn, D, b.w_qkv, D, S, 3 * D, D, kEpiQkvRope, e1, st))) return rc;
+      if ((rc = launch_gemm(ctx, x, D, b.w_qkv, D, S, 3 * D, D, kEpiQkvRope, e1, st))) return rc;
     }
     {
       ProfScope ps(ctx, kProfAttention, st);
@@ -433,26 +459,23 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
       if (rc) return rc;
     }
     GemmEpilogue e2{};
-    e2.bias = b.b_proj; e2.residual = x; e2.ld_res = D; e2.out = x; e2.ldc = D;
+    e2.bias = b.b_proj; e2.residual = x; e2.ld_res = D; e2.out = x; e2.ldc = D; e2.stat_part = st_a; e2.stat_slots = slots;
     {
       ProfScope ps(ctx, kProfProj, st);
       if ((rc = launch_gemm(ctx, attn, D, b.w_proj, D, S, D, D, KOCR_EPI_BIAS_RESIDUAL, e2, st))) return rc;
     }
-    // norm2 -> mlp
-    {
-      ProfScope ps(ctx, kProfNorm, st);
-      if ((rc = launch_norm(x, D, b.n2w, t->q25 ? nullptr : b.n2b, xn, D, S, D, 1e-6f, t->q25, st))) return rc;
-    }
+    // [norm2 folded] fc1 (+bias, activation) -> fc2 (+bias, +residual, row statistics for the next block's norm1)
     GemmEpilogue e3{};
     e3.bias = b.b_fc1; e3.out = hbuf; e3.ldc = Fp;
+    e3.ln_part = st_a; e3.ln_c1 = b.c1_fc1; e3.ln_slots = slots; e3.ln_rms = t->q25; e3.ln_inv_dim = 1.0f / D; e3.ln_eps = 1e-6f;
     {
       ProfScope ps(ctx, kProfFc1, st);
-      if (!t->q25) rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, Fp, D, KOCR_EPI_BIAS_QUICKGELU, e3, st);
-      else rc = launch_gemm(ctx, xn, D, b.w_fc1, D, S, 2 * Fp, D, KOCR_EPI_BIAS_SWIGLU, e3, st);
+      if (!t->q25) rc = launch_gemm(ctx, x, D, b.w_fc1, D, S, Fp, D, KOCR_EPI_BIAS_QUICKGELU, e3, st);
+      else rc = launch_gemm(ctx, x, D, b.w_fc1, D, S, 2 * Fp, D, KOCR_EPI_BIAS_SWIGLU, e3, st);
       if (rc) return rc;
     }
     GemmEpilogue e4{};
-    e4.bias = b.b_fc2; e4.residual = x; e4.ld_res = D; e4.out = x; e4.ldc = D;
+    e4.bias = b.b_fc2; e4.residual = x; e4.ld_res = D; e4.out = x; e4.ldc = D; e4.stat_part = st_b; e4.stat_slots = slots;
     {
       ProfScope ps(ctx, kProfFc2, st);
       if ((rc = launch_gemm(ctx, hbuf, Fp, b.w_fc2, Fp, S, D, Fp, KOCR_EPI_BIAS_RESIDUAL, e4, st))) return rc;
