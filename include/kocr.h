@@ -162,6 +162,27 @@ KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int 
                        int n_images, void* out, void* hidden_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
+/* ------------------------------------------------------------------ LLM hand-off */
+
+/* Host planning (no GPU): 3-D M-RoPE position ids of a text+image prompt.  Stands in for
+ * Qwen2VLModel.get_rope_index (HF modeling_qwen2_vl.py:990-1092, get_vision_position_ids :934-988), reached from
+ * karanta/training/ocr_training.py:86,670 (model(**batch)) and test_trained_model.py:91 (model.generate).
+ *   input_ids [batch*seq_len] int64; attention_mask [batch*seq_len] int64 or NULL; image runs are the maximal runs of
+ *   image_token_id among the unmasked tokens, consumed in order against image_grid_thw (t must be 1: still pages).
+ *   position_ids [3*batch*seq_len] int64 (masked positions stay 0), deltas [batch] int64 (max position + 1 - length).
+ * KOCR_ERR_INVALID when the number of image runs / their lengths disagree with image_grid_thw. */
+KOCR_API int kocr_mrope_position_ids(const int64_t* input_ids, const int64_t* attention_mask, int batch, int seq_len,
+                                     const int64_t* image_grid_thw, int n_images, int64_t image_token_id, int merge,
+                                     int64_t* position_ids, int64_t* deltas);
+
+/* inputs_embeds.masked_scatter(input_ids == image_token_id, image_embeds) on the device, in place.  Stands in for
+ * get_placeholder_mask + masked_scatter (HF modeling_qwen2_vl.py:1138-1177 and the forward's
+ * `inputs_embeds.masked_scatter(image_mask, image_embeds)`).
+ *   inputs_embeds: DEVICE bf16 [batch*seq_len, hidden]; image_embeds: DEVICE bf16 [n_rows, hidden]; input_ids: HOST.
+ * KOCR_ERR_INVALID ("Image features and image tokens do not match, ...") when the placeholder count != n_rows. */
+KOCR_API int kocr_scatter_image_embeds(KocrCtx* ctx, void* inputs_embeds, const void* image_embeds, int64_t n_rows, int hidden,
+                                       const int64_t* input_ids, int batch, int seq_len, int64_t image_token_id, void* stream);
+
 /* Number of kernels the last kocr_preprocess / kocr_tower_forward on this thread launched. */
 KOCR_API int64_t kocr_last_launch_count(void);
 

@@ -281,3 +281,49 @@ def flops_per_batch(cfg: TowerConfig, grid_thw) -> float:
     m = cfg.spatial_merge_size ** 2
     total += 2.0 * (N / m) * (m * D) ** 2 + 2.0 * (N / m) * (m * D) * O
     return total
+
+
+# ---------------------------------------------------------------- LLM hand-off
+
+def mrope_position_ids(input_ids, image_grid_thw, attention_mask=None, image_token_id=151655, merge=2):
+    """numpy restatement of Qwen2VLModel.get_rope_index for still images (HF modeling_qwen2_vl.py:990-1092 with
+    get_vision_position_ids :934-988): -> (position_ids int64 [3,B,L], deltas int64 [B,1])."""
+    ids = np.asarray(input_ids, dtype=np.int64)
+    B, L = ids.shape
+    pos = np.zeros((3, B, L), dtype=np.int64)
+    deltas = np.zeros((B, 1), dtype=np.int64)
+    grids = iter(np.asarray(image_grid_thw, dtype=np.int64).reshape(-1, 3).tolist())
+    for b in range(B):
+        keep = np.arange(L) if attention_mask is None else np.nonzero(np.asarray(attention_mask)[b])[0]
+        cur_ids = ids[b, keep]
+        is_img = (cur_ids == image_token_id).tolist()
+        chunks, cur, k = [], 0, 0
+        while k < len(cur_ids):
+            e = k
+            while e < len(cur_ids) and is_img[e] == is_img[k]:
+                e += 1
+            if not is_img[k]:
+                chunks.append(np.tile(np.arange(e - k) + cur, (3, 1)))
+                cur += e - k
+            else:
+                t, gh, gw = next(grids)
+                gh, gw = gh // merge, gw // merge
+                assert t == 1 and gh * gw == e - k
+                w = np.tile(np.arange(cur, cur + gw), gh * t)
+                h = np.repeat(np.arange(cur, cur + gh), gw * t)
+                chunks.append(np.stack([np.full(gh * gw * t, cur), h, w]))
+                cur += max(gh, gw)
+            k = e
+        llm = np.concatenate(chunks, axis=1)
+        pos[:, b, keep] = llm
+        deltas[b, 0] = llm.max() + 1 - len(cur_ids)
+    return pos, deltas
+
+
+def scatter_image_features(inputs_embeds: torch.Tensor, input_ids, image_embeds: torch.Tensor, image_token_id=151655):
+    """inputs_embeds.masked_scatter(input_ids == image_token_id, image_embeds) (HF modeling_qwen2_vl.py:1138-1177)."""
+    mask = (torch.as_tensor(input_ids) == image_token_id)
+    if int(mask.sum()) != image_embeds.shape[0]:
+        raise ValueError(f"Image features and image tokens do not match, tokens: {int(mask.sum())}, features: {image_embeds.shape[0]}")
+    m = mask.unsqueeze(-1).expand_as(inputs_embeds)
+    return inputs_embeds.masked_scatter(m, image_embeds.to(inputs_embeds.dtype))

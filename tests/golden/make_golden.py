@@ -206,7 +206,7 @@ def g5_embeddings():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["g1", "g3", "g24", "g5"]
+    which = sys.argv[1:] or ["g1", "g3", "g24", "g5", "g6"]
     if "g1" in which:
         g1_smart_resize()
     if "g3" in which:
@@ -215,3 +215,5 @@ if __name__ == "__main__":
         g2_g4_pixel_values()
     if "g5" in which:
         g5_embeddings()
+    if "g6" in which:
+        g6_llm_handoff()
