@@ -44,8 +44,23 @@ def peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def make_pages(n, distinct=8):
+MIXED_SHAPES = [(1288, 420), (640, 880), (256, 256), (1288, 910), (1288, 995), (995, 1288)]
+WORKLOADS = {
+    "c2": WORKLOAD,
+    "c3": ("C3: Qwen2.5-VL-7B vision tower (depth 32, D 1280, 16 heads, gated mlp 3420, out 3584, 112 px windows, full attention "
+           "in blocks 7/15/23/31), 64 synthetic letter pages u8[3,1288,995] per step per GPU"),
+    "c4": ("C4: Qwen2-VL-7B vision tower, mixed-aspect varlen batch of 64 pages per step per GPU drawn (seeded) from "
+           "1288x420, 640x880, 256x256, 1288x910, 1288x995, 995x1288"),
+}
+
+
+def make_pages(n, distinct=8, workload="c2"):
     from tests.synth import synth_page
+    if workload == "c4":
+        rng = np.random.default_rng(4)
+        picks = rng.integers(0, len(MIXED_SHAPES), n)
+        cache = {}
+        return [cache.setdefault(int(k), synth_page(*MIXED_SHAPES[int(k)], 4000 + int(k))) for k in picks]
     base = [synth_page(PAGE_H, PAGE_W, 1234 + i) for i in range(min(n, distinct))]
     return [base[i % len(base)] for i in range(n)]
 
@@ -198,17 +213,29 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = vo.qwen2_vl_7b()
-    tower = KarantaVisionTower(dict(arch="qwen2_vl", depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
-                                    mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden), device=dev)
+    cfg = vo.qwen2_5_vl_7b() if args.workload == "c3" else vo.qwen2_vl_7b()
+    tower = KarantaVisionTower(dict(arch=cfg.arch, depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
+                                    mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden, window_size=cfg.window_size,
+                                    fullatt_block_indexes=list(cfg.fullatt_block_indexes)), device=dev)
     tower.load_state_dict(vo.init_weights(cfg, seed=0))
     enc = PageEncoder(tower, MIN_PIXELS, MAX_PIXELS)
     n_pages = args.pages
-    pages = make_pages(n_pages)
-    grid_ref = [[1, 92, 72]] * n_pages
+    pages = make_pages(n_pages, workload=args.workload)
+    from karanta_ocr_b200 import smart_resize
+    grid_ref = []
+    for p in pages:
+        rh, rw = smart_resize(p.shape[1], p.shape[2], 28, MIN_PIXELS, MAX_PIXELS)
+        grid_ref.append([1, rh // 14, rw // 14])
     flops_step = vo.flops_per_batch(cfg, grid_ref)
-    flops_attn_launch = 4.0 * cfg.embed_dim * n_pages * (92 * 72) ** 2
-    N = 92 * 72 * n_pages
+    N = int(sum(g[1] * g[2] for g in grid_ref))
+    l2_full = float(sum((g[1] * g[2]) ** 2 for g in grid_ref))
+    attn_flops_step = 4.0 * cfg.embed_dim * l2_full * cfg.depth
+    if cfg.arch == "qwen2_5_vl":
+        _, cuw = vo.window_index(np.asarray(grid_ref), cfg.window_size, 2, 14)
+        l2_win = float(((cuw[1:].astype(np.int64) - cuw[:-1]) ** 2).sum())
+        nf = len(cfg.fullatt_block_indexes)
+        attn_flops_step = 4.0 * cfg.embed_dim * (l2_full * nf + l2_win * (cfg.depth - nf))
+    flops_attn_launch = attn_flops_step / cfg.depth
 
     # device-resident inputs for `value`; pinned host inputs for `e2e`
     d_pages = [torch.from_numpy(p).to(dev) for p in pages]
@@ -268,14 +295,15 @@ def run_gpu(args):
                      for i in range(ncls) if cls_n[i]}
         dom = max(per_class, key=lambda k: per_class[k]["ms_total"])
         D, F = cfg.embed_dim, cfg.mlp_hidden
+        fc1_mult = 2.0 if cfg.arch == "qwen2_5_vl" else 1.0  # gate and up projections
         flops_by_class = {"attention": flops_attn_launch, "gemm_qkv_rope": 2.0 * N * D * 3 * D, "gemm_proj": 2.0 * N * D * D,
-                          "gemm_fc1": 2.0 * N * D * F, "gemm_fc2": 2.0 * N * D * F, "gemm_patch_embed": 2.0 * N * 1176 * D}
+                          "gemm_fc1": 2.0 * N * D * F * fc1_mult, "gemm_fc2": 2.0 * N * D * F, "gemm_patch_embed": 2.0 * N * 1176 * D}
         for k, v in per_class.items():
             if k in flops_by_class:
                 v["tflops"] = flops_by_class[k] / (v["ms_per_launch"] * 1e-3) / 1e12
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tp) and n_pages == PAGES_PER_STEP:  # ncu dram__bytes_read+write per launch at this batch size
+        if os.path.exists(tp) and n_pages == PAGES_PER_STEP and args.workload == "c2":  # ncu dram__bytes_read+write per launch at this batch size
             tj = json.load(open(tp))
             traffic, traffic_src = tj["dram_bytes_per_launch"].get(dom), tj["source"]
         if dom in flops_by_class:
@@ -287,12 +315,12 @@ def run_gpu(args):
         else:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
         pre = per_class.get("preprocess")
-        pre_bytes = n_pages * (3 * PAGE_H * PAGE_W + 6624 * 1176 * 2)
+        pre_bytes = int(sum(p.size for p in pages)) + N * 1176 * 2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pages_per_step_per_gpu": n_pages, "parallelism": f"page-sharded replicas x{world}, no collective",
+            "config": {"workload": WORKLOADS[args.workload], "pages_per_step_per_gpu": n_pages, "patches_per_step_per_gpu": N, "parallelism": f"page-sharded replicas x{world}, no collective",
                        "l2": "per-step working set ~11 GB (activations 1.09 GB per tensor) >> 126 MB L2, no flush needed",
                        "weights": "seeded random init (no checkpoints offline)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -309,7 +337,7 @@ def run_gpu(args):
                                if pre else None),
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
             run_once, kind, desc = cpu_reference_sample()
             run_once()
             spp = float(np.mean([run_once() for _ in range(2)]))
@@ -327,6 +355,8 @@ def main():
     ap.add_argument("--impl", default="kocr", choices=["kocr", "reference"])
     ap.add_argument("--pages", type=int, default=PAGES_PER_STEP, help="pages per step per GPU (C2 = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 = the metric's configuration (default); c3 / c4 = the other BASELINE.json configs, for the record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
