@@ -33,8 +33,15 @@ static constexpr int kSub = 64;              // keys per score sub-step (S and P
 static constexpr int kChunkBytes = kTileRows * 32;  // 4096
 static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
 static constexpr int kKvStages = 3;
-static constexpr int kAttnThreads = 384;
-static constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKvStages * kTileBytes + 512 + 1024;
+#ifndef KOCR_COL_SPLIT
+#define KOCR_COL_SPLIT 1
+#endif
+static constexpr int kColSplit = KOCR_COL_SPLIT;        // softmax warps sharing a block of 32 query rows
+static constexpr int kColsPer = kSub / kColSplit;        // score columns per thread per sub-step
+static constexpr int kOColsPer = kHd / kColSplit;        // output columns per thread
+static constexpr int kAttnThreads = 128 + 256 * kColSplit;
+static constexpr int kXchBytes = 2 * 2 * kColSplit * kTileRows * 4;  // [parity][tile][share][row] f32 exchange buffer
+static constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKvStages * kTileBytes + 512 + kXchBytes + 1024;
 #ifndef KOCR_POLY_EVERY
 #define KOCR_POLY_EVERY 4
 #endif
@@ -74,6 +81,29 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  static_assert(N == 80 || N == 40, "unsupported column count");
+  if constexpr (N == 80) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) tmem_ld_x16(taddr + c * 16, r + c * 16);
+  } else {
+    tmem_ld_x16(taddr, r);
+    tmem_ld_x16(taddr + 16, r + 16);
+    tmem_ld_x8(taddr + 32, r + 32);
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N == 80) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) tmem_st_x16(taddr + c * 16, r + c * 16);
+  } else {
+    tmem_st_x16(taddr, r);
+    tmem_st_x16(taddr + 16, r + 16);
+    tmem_st_x8(taddr + 32, r + 32);
+  }
+}
 __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -124,6 +154,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   uint64_t* p_full = s_full + 4;           // [tile][buffer] = 4
   uint64_t* o_done = p_full + 4;           // [tile][sub-step parity] = 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -144,7 +175,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 128 * kColSplit);
       mbar_init(&o_done[t], 1);
     }
     fence_barrier_init();
@@ -158,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   // first 32 columns of S[t][b]; O[t] (80 columns) at 256 + t*128.
 
   if (warp < 4) {
-    setmaxnreg_dec<96>();
+    if constexpr (kColSplit == 1) setmaxnreg_dec<96>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane issues)
       const int q_begin = (int)uniform_u32(w.q_begin), kv_begin = (int)uniform_u32(w.kv_begin);
@@ -248,13 +279,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    setmaxnreg_inc<200>();  // 128*96 + 256*200 <= 384*168 (the launch allocation): inc can never starve
-    const int t = (warp - 4) >> 2;   // query tile
-    const int qtr = warp & 3;        // TMEM lane quarter
-    const int r = qtr * 32 + lane;   // row within the tile
+    // ------------------------------------------------------------------ softmax warps
+    // kColSplit warps share each block of 32 query rows (same TMEM lane quarter) and split the 64 score columns of a
+    // sub-step between them: more resident warps per scheduler to hide the MUFU / TMEM / barrier latencies, at the price
+    // of one 64-thread named barrier per sub-step to exchange the partial row max. Row sums stay partial until the end.
+    if constexpr (kColSplit == 1) setmaxnreg_inc<200>();  // 128*96 + 256*200 <= 384*168 (the launch allocation)
+    const int sw = warp - 4;
+    const int t = sw / (4 * kColSplit);      // query tile
+    const int ch = (sw >> 2) % kColSplit;    // which share of the score columns
+    const int qtr = warp & 3;                // TMEM lane quarter
+    const int r = qtr * 32 + lane;           // row within the tile
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
+    const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off + ch * kOColsPer;
+    const int bar_id = 1 + t * 4 + qtr;      // named barrier of the warps that share these 32 rows
     float m_ref = -INFINITY, l = 0.f;
     int w_lo = 0, w_hi = 0;  // this row's window, as key indices relative to kv_begin
     if (kWin) {
@@ -265,64 +302,68 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         w_hi = wb.y - w.kv_begin;
       }
     }
-#if KOCR_PREFETCH_S
-    uint32_t sr[kSub];
-    mbar_wait(&s_full[t * 2], 0);
-    tc_fence_after();
-    tmem_ld_x32(tmem_base + t * 128 + lane_off, sr);
-    tmem_ld_x32(tmem_base + t * 128 + lane_off + 32, sr + 32);
-#endif
     for (int i = 0; i < n_sub; ++i) {
       const uint32_t t_s = tmem_base + t * 128 + (i & 1) * kSub + lane_off;
-#if KOCR_PREFETCH_S
-      tc_wait_ld();  // S(i) was requested at the tail of the previous iteration
-#else
       mbar_wait(&s_full[t * 2 + (i & 1)], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t sr[kSub];
-      tmem_ld_x32(t_s, sr);
-      tmem_ld_x32(t_s + 32, sr + 32);
+      uint32_t sr[kColsPer];
+      if constexpr (kColsPer == 64) {
+        tmem_ld_x32(t_s, sr);
+        tmem_ld_x32(t_s + 32, sr + 32);
+      } else {
+        tmem_ld_x32(t_s + ch * kColsPer, sr);
+      }
       tc_wait_ld();
-#endif
+      const int c0 = i * kSub + ch * kColsPer;  // key index (relative to kv_begin) of this thread's first column
       if (kWin) {
-        const int c_lo = w_lo - i * kSub, c_hi = w_hi - i * kSub;  // valid columns of this sub-step: [c_lo, c_hi)
-        if (c_lo > 0 || c_hi < kSub) {
+        const int c_lo = w_lo - c0, c_hi = w_hi - c0;  // valid columns: [c_lo, c_hi)
+        if (c_lo > 0 || c_hi < kColsPer) {
 #pragma unroll
-          for (int c = 0; c < kSub; ++c)
+          for (int c = 0; c < kColsPer; ++c)
             if (c < c_lo || c >= c_hi) sr[c] = 0xff800000u;  // -inf
         }
       } else {
-        const int valid = w.kv_len - i * kSub;
-        if (valid < kSub) {
+        const int valid = w.kv_len - c0;
+        if (valid < kColsPer) {
 #pragma unroll
-          for (int c = 0; c < kSub; ++c)
+          for (int c = 0; c < kColsPer; ++c)
             if (c >= valid) sr[c] = 0xff800000u;  // -inf
         }
       }
-      // row max: 4 independent FMNMX3 chains
-      float mxa[4];
+      // row max: independent FMNMX3 chains of 16 columns
+      float mxa[kColsPer / 16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < kColsPer / 16; ++g) {
         mxa[g] = max3(__uint_as_float(sr[16 * g]), __uint_as_float(sr[16 * g + 1]), __uint_as_float(sr[16 * g + 2]));
 #pragma unroll
         for (int c = 3; c < 15; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[16 * g + c]), __uint_as_float(sr[16 * g + c + 1]));
         mxa[g] = fmaxf(mxa[g], __uint_as_float(sr[16 * g + 15]));
       }
-      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      float mx = mxa[0];
+#pragma unroll
+      for (int g = 1; g < kColsPer / 16; ++g) mx = fmaxf(mx, mxa[g]);
+      if constexpr (kColSplit > 1) {
+        // exchange the partial max with the warps sharing these rows (buffer by sub-step parity: one barrier suffices)
+        float* xb = xch + ((i & 1) * 2 + t) * kColSplit * kTileRows;
+        xb[ch * kTileRows + r] = mx;
+        named_bar_sync(bar_id, 32 * kColSplit);
+#pragma unroll
+        for (int o = 0; o < kColSplit; ++o) mx = fmaxf(mx, xb[o * kTileRows + r]);
+      }
       float alpha = 1.0f;
       const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first sub-step (m_ref = -inf)
       if (grow) {
         alpha = ex2(m_ref - mx);  // 0 on the first sub-step
         m_ref = mx;
       }
-      // p = 2^(s - m): packed f32x2 subtract and 4 independent packed row-sum accumulators
+      // p = 2^(s - m): packed f32x2 subtract and independent packed row-sum accumulators
       // (a row whose keys so far are all masked still has m_ref = -inf: subtract 0 so its p are 2^-inf = 0, not NaN)
-      const float neg_m = (kWin && m_ref == -INFINITY) ? 0.f : -m_ref;
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[kSub / 2];
+      uint32_t pk[kColsPer / 2];
 #pragma unroll
-      for (int c = 0; c < kSub / 2; ++c) {
+      for (int c = 0; c < kColsPer / 2; ++c) {
         const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
         uint64_t p2;
         if (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) {
@@ -345,56 +386,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         sum = (a0 + a1) + (b0 + b1);
       }
       l = l * alpha + sum;
-      tmem_st_x16(t_s, pk);
-      tmem_st_x16(t_s + 16, pk + 16);
-#if KOCR_PREFETCH_S
-      // the score registers are dead: request S(i+1) now so its TMEM latency (and the s_full check) overlaps the
-      // P store, the O bookkeeping and the p_full hand-off below
-      if (i + 1 < n_sub) {
-        mbar_wait(&s_full[t * 2 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_n = tmem_base + t * 128 + ((i + 1) & 1) * kSub + lane_off;
-        tmem_ld_x32(t_n, sr);
-        tmem_ld_x32(t_n + 32, sr + 32);
+      if constexpr (kColsPer == 64) {
+        tmem_st_x16(t_s, pk);
+        tmem_st_x16(t_s + 16, pk + 16);
+      } else {
+        tmem_st_x16(t_s + ch * (kColsPer / 2), pk);
       }
-#endif
       // P.V completions are signalled on two alternating barriers per tile, o_done[t][i&1], so a parity wait stays
       // unambiguous as long as every completion is observed within two sub-steps. P_{i-2} V (issued two softmaxes ago)
       // is observed here every sub-step - normally free - and P_{i-1} V only when O really has to be rescaled.
       if (i > 1) mbar_wait(&o_done[t * 2 + (i & 1)], ((i - 2) >> 1) & 1);
       if (i > 0) {
-        // O_t holds P V of sub-steps < i relative to the old reference; bring it to the new one before P_i V is added
+        // O_t holds P V of sub-steps < i relative to the old reference; bring this warp's share of its columns to the
+        // new one before P_i V is added (the warps sharing the rows saw the same max and take the same decision)
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&o_done[t * 2 + ((i - 1) & 1)], ((i - 1) >> 1) & 1);
           tc_fence_after();
-          uint32_t o[80];
-#pragma unroll
-          for (int c = 0; c < 5; ++c) tmem_ld_x16(t_o + c * 16, o + c * 16);
+          uint32_t o[kOColsPer];
+          tmem_ld_cols<kOColsPer>(t_o, o);
           tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 80; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-#pragma unroll
-          for (int c = 0; c < 5; ++c) tmem_st_x16(t_o + c * 16, o + c * 16);
+          for (int c = 0; c < kOColsPer; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st_cols<kOColsPer>(t_o, o);
         }
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[t * 2 + (i & 1)]);
     }
-    // ---- epilogue: O / l -> bf16 -> out[row, head*80 ..]
+    // ---- epilogue: O / l -> bf16 -> out[row, head*80 + this warp's columns]
+    if constexpr (kColSplit > 1) {
+      float* xb = xch + (((n_sub & 1) * 2) + t) * kColSplit * kTileRows;  // the buffer the last sub-step did not use
+      xb[ch * kTileRows + r] = l;
+      named_bar_sync(bar_id, 32 * kColSplit);
+      l = 0.f;
+#pragma unroll
+      for (int o = 0; o < kColSplit; ++o) l += xb[o * kTileRows + r];
+    }
     if (n_sub > 1) mbar_wait(&o_done[t * 2 + ((n_sub - 2) & 1)], ((n_sub - 2) >> 1) & 1);
     mbar_wait(&o_done[t * 2 + ((n_sub - 1) & 1)], ((n_sub - 1) >> 1) & 1);
     tc_fence_after();
-    uint32_t o[80];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) tmem_ld_x16(t_o + c * 16, o + c * 16);
+    uint32_t o[kOColsPer];
+    tmem_ld_cols<kOColsPer>(t_o, o);
     tc_wait_ld();
     const float inv = 1.0f / l;
     const int qrow = t * kTileRows + r;
     if (qrow < w.q_rows) {
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(w.q_begin + qrow) * (num_heads * kHd) + head * kHd);
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(w.q_begin + qrow) * (num_heads * kHd) + head * kHd + ch * kOColsPer);
 #pragma unroll
-      for (int c = 0; c < 10; ++c) {
+      for (int c = 0; c < kOColsPer / 8; ++c) {
         const uint32_t* x = o + c * 8;
         dst[c] = make_uint4(pack_bf16(__uint_as_float(x[0]) * inv, __uint_as_float(x[1]) * inv),
                             pack_bf16(__uint_as_float(x[2]) * inv, __uint_as_float(x[3]) * inv),
