@@ -156,17 +156,22 @@ class KarantaImageProcessor:
             for _, p in host:
                 offs.append(total)
                 total += (p[0].numel() + 255) // 256 * 256
-            if self._pinned is None or self._pinned.numel() < total:
-                self._pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
-                self._pinned_ev = None
-            if self._pinned_ev is not None:
-                self._pinned_ev.synchronize()
-            for (i, p), o in zip(host, offs):
-                self._pinned[o:o + p[0].numel()].copy_(p[0].reshape(-1))
             dbuf = torch.empty(total, dtype=torch.uint8, device=dev)
-            dbuf.copy_(self._pinned[:total], non_blocking=True)
-            self._pinned_ev = torch.cuda.Event()
-            self._pinned_ev.record(torch.cuda.current_stream(dev))
+            if all(p[0].is_pinned() for _, p in host):
+                # already page-locked (bulk encode keeps its pages pinned): copy each page straight into the packed buffer
+                for (i, p), o in zip(host, offs):
+                    dbuf[o:o + p[0].numel()].copy_(p[0].reshape(-1), non_blocking=True)
+            else:
+                if self._pinned is None or self._pinned.numel() < total:
+                    self._pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+                    self._pinned_ev = None
+                if self._pinned_ev is not None:
+                    self._pinned_ev.synchronize()
+                for (i, p), o in zip(host, offs):
+                    self._pinned[o:o + p[0].numel()].copy_(p[0].reshape(-1))
+                dbuf.copy_(self._pinned[:total], non_blocking=True)
+                self._pinned_ev = torch.cuda.Event()
+                self._pinned_ev.record(torch.cuda.current_stream(dev))
             keep.append(dbuf)
             for (i, p), o in zip(host, offs):
                 ptrs[i] = dbuf.data_ptr() + o

@@ -97,6 +97,34 @@ class PageEncoder:
         return emb, grid
 
     @torch.no_grad()
+    def encode_to_host_async(self, pages, out_host: torch.Tensor):
+        """Pipelined end-to-end call for bulk encoding: the H2D copy + preprocess run on an input stream, the tower on the
+        caller's stream, the D2H of the embeddings on an output stream, chained by events, so consecutive calls overlap
+        their copies with each other's compute. Returns (event that completes when out_host is filled, grid, n_rows);
+        the caller must not reuse `out_host` (or its pages) before that event."""
+        dev = self.tower.device
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._s_in):
+            pv, grid = self.processor.preprocess_device(pages, out_dtype=torch.bfloat16)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self._s_in)
+        cur.wait_event(ev_in)
+        pv.record_stream(cur)
+        emb = self.tower(pv, grid_thw=grid)
+        self.last_launch_count = 1 + self.tower.last_launch_count
+        ev_c = torch.cuda.Event()
+        ev_c.record(cur)
+        self._s_out.wait_event(ev_c)
+        with torch.cuda.stream(self._s_out):
+            out_host[: emb.shape[0]].copy_(emb, non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record(self._s_out)
+        emb.record_stream(self._s_out)
+        return ev_out, grid, emb.shape[0]
+
+    @torch.no_grad()
     def encode_to_host(self, pages, out_host: torch.Tensor | None = None):
         """End-to-end call: host pages in, embeddings in (pinned) host memory out."""
         emb, grid = self.encode(pages)
