@@ -58,8 +58,11 @@ _DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.flo
 
 
 class KarantaVisionTower(torch.nn.Module):
-    def __init__(self, config, device=None):
+    def __init__(self, config, device=None, hf_output: bool = False):
         super().__init__()
+        # transformers 5.x towers return BaseModelOutputWithPooling (get_image_features reads .pooler_output);
+        # 4.53.3 (the reference's pin) and vLLM return the merged tensor. hf_output selects the former.
+        self.hf_output = bool(hf_output)
         if not torch.cuda.is_available():
             raise RuntimeError("KarantaVisionTower needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.cfg = normalize_config(config)
@@ -178,9 +181,37 @@ class KarantaVisionTower(torch.nn.Module):
             _lib.check(rc)
             self.last_launch_count = int(_lib.load().kocr_last_launch_count())
             x.record_stream(torch.cuda.current_stream(dev))
+        if self.hf_output:
+            from transformers.modeling_outputs import BaseModelOutputWithPooling
+            return BaseModelOutputWithPooling(last_hidden_state=hid, pooler_output=out)
         if return_hidden:
             return out, hid
         return out
+
+    @classmethod
+    def replace_visual(cls, model, device=None):
+        """Swap a loaded Qwen2-VL / Qwen2.5-VL model's vision tower for this one (inference): finds `model.visual`
+        (transformers 4.53.3, vLLM) or `model.model.visual` (transformers 5.x), builds the tower from its config and
+        state dict, and assigns it in place. Returns the new tower."""
+        owner, hf5 = None, False
+        if hasattr(model, "visual"):
+            owner = model
+        elif hasattr(model, "model") and hasattr(model.model, "visual"):
+            owner, hf5 = model.model, True
+        if owner is None:
+            raise ValueError("model has no `visual` / `model.visual` module")
+        old = owner.visual
+        if not hf5:
+            try:  # a 5.x Qwen2VLModel used directly also returns the structured output
+                import transformers
+                hf5 = int(transformers.__version__.split(".")[0]) >= 5 and old.__class__.__module__.startswith("transformers.")
+            except Exception:
+                hf5 = False
+        dev = device if device is not None else next(old.parameters()).device
+        tower = cls(old.config, device=dev, hf_output=hf5)
+        tower.load_state_dict(old.state_dict())
+        owner.visual = tower
+        return tower
 
     def split_per_image(self, embeddings: torch.Tensor, grid_thw):
         """get_image_features' per-image split (modeling_qwen2_vl.py:1132-1134)."""

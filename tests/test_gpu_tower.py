@@ -143,3 +143,29 @@ def test_batch_equals_single_pages():
     for i in (0, 3):
         one, _ = enc.encode([pages[i]])
         assert torch.equal(one, parts[i])
+
+
+def test_drop_in_for_transformers_model():
+    """The real call site: a transformers Qwen2VLModel (tiny widths, seeded) has its `visual` replaced in place and
+    `get_image_features(pixel_values, image_grid_thw)` - what model(**batch) calls - is compared with the original."""
+    tf = pytest.importorskip("transformers")
+    from transformers.models.qwen2_vl.configuration_qwen2_vl import Qwen2VLConfig
+    from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VLModel
+    from karanta_ocr_b200 import KarantaImageProcessor, KarantaVisionTower
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(text_config=dict(hidden_size=256, intermediate_size=256, num_hidden_layers=1, num_attention_heads=4,
+                                         num_key_value_heads=2, vocab_size=152000,
+                                         rope_scaling={"type": "mrope", "mrope_section": [8, 12, 12]}),
+                        vision_config=dict(depth=2, embed_dim=160, hidden_size=256, num_heads=2, mlp_ratio=4))
+    model = Qwen2VLModel(cfg).eval().to("cuda", torch.bfloat16)
+    pages = [synth_page(140, 112, 81), synth_page(56, 168, 82)]
+    feats = KarantaImageProcessor(min_pixels=3136, max_pixels=CKPT_MAX, device="cuda")(images=pages)
+    pv, grid = feats["pixel_values"], feats["image_grid_thw"].to("cuda")
+    with torch.no_grad():
+        ref32 = model.float().get_image_features(pv, grid).pooler_output       # fp32 on the GPU: the tolerance anchor
+        model.to(torch.bfloat16)
+        tower = KarantaVisionTower.replace_visual(model)
+        assert model.visual is tower
+        got = model.get_image_features(pv.to(torch.bfloat16), grid).pooler_output
+    assert len(got) == 2 and [g.shape for g in got] == [r.shape for r in ref32]
+    _check(torch.cat(list(got)), torch.cat(list(ref32)).cpu(), grid.cpu().numpy(), "hf_drop_in")
