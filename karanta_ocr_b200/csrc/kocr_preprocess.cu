@@ -39,6 +39,7 @@ struct PageJob {
 static constexpr int kStrip = 28;       // output rows per tile = patch * merge
 static constexpr int kPatchDim = 1176;  // 3 * 2 * 14 * 14
 static constexpr int kThreads = 256;
+static constexpr int kMaxStageRows = 768;  // staged input rows per tile (3 planes x up to 256 rows)
 static constexpr int kRB = 14;           // rows of horizontal-pass accumulators held in registers per thread
 
 // 1-D bulk async copy shared -> global (TMA engine, no tensor map): size and both addresses multiples of 16 bytes
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float lut[768];
   __shared__ PageJob job;
+  __shared__ uintptr_t row_ptr[kMaxStageRows];
   for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -116,6 +118,12 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
       const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
       const int nrows = nseg * rows_in;
       constexpr int kWarps = kThreads / 32, kRowsInFlight = 6;
+      // the 64-bit address of every staged row is worked out once per tile (one thread per row), not per lane and word
+      for (int sr = threadIdx.x; sr < nrows; sr += kThreads) {
+        const int sg = sr >= 2 * rows_in ? 2 : (sr >= rows_in ? 1 : 0);
+        row_ptr[sr] = reinterpret_cast<uintptr_t>(seg0 + sg * j.chan_stride + (long long)(sr - sg * rows_in) * j.row_pitch);
+      }
+      __syncthreads();
       // warp per staged row, lanes over its words; kRowsInFlight rows are requested before the first is consumed, and
       // the upper word of each funnel shift comes from the neighbouring lane instead of a second load
       for (int wd0 = 0; wd0 < wpr; wd0 += 32) {
@@ -129,8 +137,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
             lo[b] = nx[b] = 0u;
             sh[b] = 0;
             if (sr < nrows) {
-              const int sg = sr >= 2 * rows_in ? 2 : (sr >= rows_in ? 1 : 0);
-              const uintptr_t p = reinterpret_cast<uintptr_t>(seg0 + sg * j.chan_stride + (long long)(sr - sg * rows_in) * j.row_pitch);
+              const uintptr_t p = row_ptr[sr];
               const uintptr_t a = (p & ~uintptr_t(3)) + 4u * wd;
               sh[b] = (int)(p & 3) * 8;
               if (wd <= wpr && a < img_end) lo[b] = __ldg(reinterpret_cast<const uint32_t*>(a));
@@ -340,6 +347,8 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     j.out_h = oh; j.out_w = ow;
     j.token_base = tokens;
     const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
+    if ((vt[i] ? 3 : 3) * rows_in > kMaxStageRows)
+      return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: vertical downscale factor too large for one tile");
     int tw = 112;  // staged output tile: 16 tokens = 37.6 KB (bf16) / 75.3 KB (f32); keeps 3+ CTAs resident per SM
     while (tw > kStrip && 3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > kSmemBudget) tw -= kStrip;
     if (3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > 200 * 1024)
