@@ -169,3 +169,30 @@ def test_drop_in_for_transformers_model():
         got = model.get_image_features(pv.to(torch.bfloat16), grid).pooler_output
     assert len(got) == 2 and [g.shape for g in got] == [r.shape for r in ref32]
     _check(torch.cat(list(got)), torch.cat(list(ref32)).cpu(), grid.cpu().numpy(), "hf_drop_in")
+
+
+@pytest.mark.parametrize("arch", ["qwen2_vl", "qwen2_5_vl"])
+def test_norm_folding_with_outlier_channels(arch):
+    """Trained ViTs carry a few channels with very large, non-zero-mean activations. The folded LayerNorm computes
+    rstd*(x.W' - mean*c1): check it against the fp32 oracle when |mean| and a handful of channels dwarf the rest."""
+    from karanta_ocr_b200 import PageEncoder
+    cfg = vo.TowerConfig(arch, 3, 1280, 16, 5120 if arch == "qwen2_vl" else 3420, 1536, fullatt_block_indexes=(1,))
+    sd = vo.init_weights(cfg, seed=7)
+    g = torch.Generator().manual_seed(8)
+    w = sd["patch_embed.proj.weight"]
+    w[:8] *= 400.0                                   # 8 outlier channels
+    w[:] = w + 0.05 * torch.randn(1, *w.shape[1:], generator=g)  # a common component -> non-zero row mean
+    for i in range(cfg.depth):
+        sd[f"blocks.{i}.norm1.weight"][:8] *= 3.0
+    pages = [synth_page(420, 336, 91), synth_page(252, 588, 92)]
+    from karanta_ocr_b200 import KarantaVisionTower
+    tower = KarantaVisionTower(dict(arch=cfg.arch, depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
+                                    mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden, window_size=cfg.window_size,
+                                    fullatt_block_indexes=list(cfg.fullatt_block_indexes)))
+    tower.load_state_dict(sd)
+    emb, grid = PageEncoder(tower).encode(pages)
+    pv, gg = po.preprocess(pages, 3136, CKPT_MAX, po.RESIZE_ATEN)
+    x0 = torch.nn.functional.linear(torch.from_numpy(pv), sd["patch_embed.proj.weight"].reshape(1280, -1))
+    assert (x0.mean(-1).abs() / x0.std(-1)).median() > 0.02 and x0.abs().max() > 50 * x0.abs().median()  # the regime is the intended one
+    ref = vo.tower_forward(cfg, sd, torch.from_numpy(pv), gg)
+    _check(emb, ref, gg, f"outliers_{arch}")
