@@ -33,9 +33,13 @@ static constexpr int kSub = 64;              // keys per score sub-step (S and P
 static constexpr int kChunkBytes = kTileRows * 32;  // 4096
 static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
 static constexpr int kKvStages = 3;
+#ifndef KOCR_PINGPONG
+#define KOCR_PINGPONG 1
+#endif
 #ifndef KOCR_COL_SPLIT
 #define KOCR_COL_SPLIT 1
 #endif
+static constexpr bool kPingPong = KOCR_PINGPONG && KOCR_COL_SPLIT == 1;
 static constexpr int kColSplit = KOCR_COL_SPLIT;        // softmax warps sharing a block of 32 query rows
 static constexpr int kColsPer = kSub / kColSplit;        // score columns per thread per sub-step
 static constexpr int kOColsPer = kHd / kColSplit;        // output columns per thread
@@ -292,6 +296,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
     const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off + ch * kOColsPer;
     const int bar_id = 1 + t * 4 + qtr;      // named barrier of the warps that share these 32 rows
+    // Exponent phase hand-over (kPingPong): the two tiles' warps of one lane quarter sit on the same scheduler and share
+    // its MUFU unit. Left alone they run in lockstep - both in the exponent phase, then both in the TMEM / max / pack
+    // phase - and the unit idles half the time. A token passed through two 64-thread named barriers makes them alternate.
+    const int pp_mine = 1 + t * 4 + qtr, pp_other = 1 + (1 - t) * 4 + qtr;
+    if (kPingPong && t == 1) named_bar_arrive(pp_other, 64);  // tile 0 goes first
     float m_ref = -INFINITY, l = 0.f;
     int w_lo = 0, w_hi = 0;  // this row's window, as key indices relative to kv_begin
     if (kWin) {
@@ -358,7 +367,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
       // p = 2^(s - m): packed f32x2 subtract and independent packed row-sum accumulators
       // (a row whose keys so far are all masked still has m_ref = -inf: subtract 0 so its p are 2^-inf = 0, not NaN)
-      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      if (kPingPong) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");  // the exponents depend on neg_m
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[kColsPer / 2];
@@ -385,6 +395,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         unpack_f32x2(add_f32x2(acc2[2], acc2[3]), b0, b1);
         sum = (a0 + a1) + (b0 + b1);
       }
+      // hand the exponent phase to the other tile's warp. The barrier id is made to depend on the row sum (>= 0, so the
+      // sign bit adds nothing) because ptxas otherwise hoists the arrive above the exponents it is meant to follow.
+      if (kPingPong && (t == 0 || i + 1 < n_sub)) named_bar_arrive(pp_other + (int)(__float_as_uint(sum) >> 31), 64);
       l = l * alpha + sum;
       if constexpr (kColsPer == 64) {
         tmem_st_x16(t_s, pk);
