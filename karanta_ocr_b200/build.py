@@ -36,7 +36,7 @@ def build_variant(name, defines):
         out_txt, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(out_txt)
-    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"])
     return out
 
 
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
     subprocess.check_call(cmd)
     return OUT
 

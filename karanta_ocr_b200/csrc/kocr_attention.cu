@@ -8,8 +8,8 @@
 // rotated and multiplied by head_dim^-0.5 * log2(e) (fused QKV GEMM epilogue), so scores are in the log2 domain.
 //
 // CTA = one 256-row query block of one sequence and one head; 384 threads:
-//   warp 0      TMA producer: Q once, then a ring of K tiles and a ring of V tiles (128 keys each)
-//   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (SS) and O_t += P_t V (P from TMEM, V MN-major)
+//   warp 0      TMA producer: a ring of K tiles and a ring of V tiles (128 keys each)
+//   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (Q from TMEM) and O_t += P_t V (P from TMEM, V MN-major)
 //   warps 4-7   softmax of query tile 0 (rows 0..127), one row per thread
 //   warps 8-11  softmax of query tile 1 (rows 128..255)
 // Operand tiles are stored as five [128 rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
@@ -17,7 +17,8 @@
 // Scores are produced in 64-key sub-steps and double-buffered in TMEM per query tile (S[t][b], b = sub-step parity), so
 // S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe and the
 // kernel runs at the MUFU (ex2) rate, which is the binding unit for head_dim 80.
-// TMEM: S[t][b] at t*128 + b*64 (64 columns); P[t][b] (bf16) overwrites the first 32 columns of S[t][b]; O_t at 256 + t*128.
+// TMEM: S[t][b] at t*128 + b*64 (64 columns); P[t][b] (bf16) overwrites the first 32 columns of S[t][b]; O_t at 256 + t*128;
+// Q_t (bf16 pairs, 40 columns, written once by the softmax threads from global memory) at 336 + t*128.
 #include <algorithm>
 #include <vector>
 
@@ -36,16 +37,14 @@ static constexpr int kKvStages = 3;
 #ifndef KOCR_PINGPONG
 #define KOCR_PINGPONG 1
 #endif
-#ifndef KOCR_COL_SPLIT
-#define KOCR_COL_SPLIT 1
+static constexpr bool kPingPong = KOCR_PINGPONG;
+static constexpr int kAttnThreads = 384;
+static constexpr int kQCol = 256 + kHd;                    // TMEM column of Q_t within tile t's 128-column half (behind O_t)
+#ifndef KOCR_PP_AT
+#define KOCR_PP_AT 22
 #endif
-static constexpr bool kPingPong = KOCR_PINGPONG && KOCR_COL_SPLIT == 1;
-static constexpr int kColSplit = KOCR_COL_SPLIT;        // softmax warps sharing a block of 32 query rows
-static constexpr int kColsPer = kSub / kColSplit;        // score columns per thread per sub-step
-static constexpr int kOColsPer = kHd / kColSplit;        // output columns per thread
-static constexpr int kAttnThreads = 128 + 256 * kColSplit;
-static constexpr int kXchBytes = 2 * 2 * kColSplit * kTileRows * 4;  // [parity][tile][share][row] f32 exchange buffer
-static constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKvStages * kTileBytes + 512 + kXchBytes + 1024;
+static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over after this pair of columns (of 32; must be a MUFU pair)
+static constexpr int kAttnSmem = 2 * kKvStages * kTileBytes + 512 + 1024;
 #ifndef KOCR_POLY_EVERY
 #define KOCR_POLY_EVERY 4
 #endif
@@ -141,15 +140,14 @@ __device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
 // attend only the keys [win[r].x, win[r].y) of its own window; a 256-row block packs four or more windows.
 template <bool kWin>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const AttnWork* __restrict__ work, int num_heads, const int2* __restrict__ win) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                                   // 2 tiles
-  uint8_t* smem_k = smem + 2 * kTileBytes;                  // kKvStages tiles
+  uint8_t* smem_k = smem;                                   // kKvStages tiles
   uint8_t* smem_v = smem_k + kKvStages * kTileBytes;        // kKvStages tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKvStages * kTileBytes);
-  uint64_t* q_full = bars;                 // 1
+  uint64_t* q_full = bars;                 // 1 (query tile 0; tile 1's is behind the tmem slot)
   uint64_t* k_full = bars + 1;             // kKvStages
   uint64_t* k_empty = k_full + kKvStages;  // kKvStages
   uint64_t* v_full = k_empty + kKvStages;
@@ -158,7 +156,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   uint64_t* p_full = s_full + 4;           // [tile][buffer] = 4
   uint64_t* o_done = p_full + 4;           // [tile][sub-step parity] = 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  uint64_t* q_full1 = o_done + 5;
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -170,7 +168,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
-    mbar_init(q_full, 1);
+    mbar_init(q_full, 128);   // the 128 softmax threads of a tile each put their query row into TMEM
+    mbar_init(q_full1, 128);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 2);  // one tcgen05.commit from each query tile's MMA warp
@@ -179,7 +178,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128 * kColSplit);
+      mbar_init(&p_full[t], 128);
       mbar_init(&o_done[t], 1);
     }
     fence_barrier_init();
@@ -193,18 +192,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   // first 32 columns of S[t][b]; O[t] (80 columns) at 256 + t*128.
 
   if (warp < 4) {
-    if constexpr (kColSplit == 1) setmaxnreg_dec<96>();
+    setmaxnreg_dec<96>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane issues)
-      const int q_begin = (int)uniform_u32(w.q_begin), kv_begin = (int)uniform_u32(w.kv_begin);
+      const int kv_begin = (int)uniform_u32(w.kv_begin);
       const int n_kv_u = (int)uniform_u32(n_kv);
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        for (int t = 0; t < 2; ++t)
-          for (int c = 0; c < kChunks; ++c)
-            tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_qkv, q_full, col_q + c * 16, q_begin + t * kTileRows);
-      }
-      __syncwarp();
       for (int j = 0; j < n_kv_u; ++j) {
         const int s = j % kKvStages;
         const uint32_t ph = (j / kKvStages) & 1;
@@ -235,7 +227,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       const int t = warp - 1;
       const uint32_t tmem_u = uniform_u32(tmem_base);
       const int n_sub_u = (int)uniform_u32(n_sub);
-      const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16) + t * (kTileBytes >> 4);
+      const uint32_t q_tm = tmem_u + kQCol + t * 128;  // Q_t as the A operand in TMEM (bf16 pairs, 8 columns per 16 dims)
       const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
       const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kChunkBytes);  // LBO = distance between 16-column groups
       const uint32_t d_o = tmem_u + 256 + t * 128;
@@ -245,7 +237,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         const uint32_t d = tmem_u + t * 128 + (i & 1) * kSub;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
-          umma_ss_lo(d, q_lo + c * (kChunkBytes >> 4), ka + c * (kChunkBytes >> 4), hi32, idesc_s, c != 0);
+          umma_ts_lo(d, q_tm + c * 8, ka + c * (kChunkBytes >> 4), hi32, idesc_s, c != 0);
         tc_commit_elect(&s_full[t * 2 + (i & 1)]);
       };
       auto issue_pv = [&](int i) {
@@ -257,7 +249,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
           umma_ts_lo(d_o, pa + ks * 8, va + ks * (512 >> 4), hi32, idesc_o, (i > 0 || ks != 0));
         tc_commit_elect(&o_done[t * 2 + (i & 1)]);
       };
-      mbar_wait(q_full, 0);
+      mbar_wait(t == 0 ? q_full : q_full1, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0);
@@ -283,24 +275,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps
-    // kColSplit warps share each block of 32 query rows (same TMEM lane quarter) and split the 64 score columns of a
-    // sub-step between them: more resident warps per scheduler to hide the MUFU / TMEM / barrier latencies, at the price
-    // of one 64-thread named barrier per sub-step to exchange the partial row max. Row sums stay partial until the end.
-    if constexpr (kColSplit == 1) setmaxnreg_inc<200>();  // 128*96 + 256*200 <= 384*168 (the launch allocation)
+    // ------------------------------------------------------------------ softmax warps, one query row per thread
+    setmaxnreg_inc<200>();                   // 128*96 + 256*200 <= 384*168 (the launch allocation)
     const int sw = warp - 4;
-    const int t = sw / (4 * kColSplit);      // query tile
-    const int ch = (sw >> 2) % kColSplit;    // which share of the score columns
+    const int t = sw >> 2;                   // query tile
     const int qtr = warp & 3;                // TMEM lane quarter
     const int r = qtr * 32 + lane;           // row within the tile
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off + ch * kOColsPer;
-    const int bar_id = 1 + t * 4 + qtr;      // named barrier of the warps that share these 32 rows
+    const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
     // Exponent phase hand-over (kPingPong): the two tiles' warps of one lane quarter sit on the same scheduler and share
     // its MUFU unit. Left alone they run in lockstep - both in the exponent phase, then both in the TMEM / max / pack
     // phase - and the unit idles half the time. A token passed through two 64-thread named barriers makes them alternate.
     const int pp_mine = 1 + t * 4 + qtr, pp_other = 1 + (1 - t) * 4 + qtr;
     if (kPingPong && t == 1) named_bar_arrive(pp_other, 64);  // tile 0 goes first
+    {
+      // this thread's query row -> TMEM, as the A operand of S = Q K^T: Q is then read from shared memory by no MMA
+      // (a 128 x 64 x 16 MMA with both operands in shared memory is bound by its 6 KB of operand reads, not by the math)
+      uint32_t qw[kHd / 2];
+      const int qr = t * kTileRows + r;
+      if (qr < w.q_rows) {
+        const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(w.q_begin + qr) * (num_heads * 3 * kHd) + col_q);
+#pragma unroll
+        for (int c = 0; c < kHd / 8; ++c) {
+          const uint4 v = __ldg(src + c);
+          qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kHd / 2; ++c) qw[c] = 0u;
+      }
+      tmem_st_cols<kHd / 2>(tmem_base + kQCol + t * 128 + lane_off, qw);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(t == 0 ? q_full : q_full1);
+    }
     float m_ref = -INFINITY, l = 0.f;
     int w_lo = 0, w_hi = 0;  // this row's window, as key indices relative to kv_begin
     if (kWin) {
@@ -312,37 +320,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
     }
     for (int i = 0; i < n_sub; ++i) {
-      const uint32_t t_s = tmem_base + t * 128 + (i & 1) * kSub + lane_off;
-      mbar_wait(&s_full[t * 2 + (i & 1)], (i >> 1) & 1);
+      const int b = i & 1;                    // S/P buffer and barrier slot of this sub-step
+      const uint32_t ph = (i >> 1) & 1;      // phase of s_full / p_full / o_done[b] for this sub-step
+      const uint32_t t_s = tmem_base + t * 128 + b * kSub + lane_off;
+      mbar_wait(&s_full[t * 2 + b], ph);
       tc_fence_after();
-      uint32_t sr[kColsPer];
-      if constexpr (kColsPer == 64) {
-        tmem_ld_x32(t_s, sr);
-        tmem_ld_x32(t_s + 32, sr + 32);
-      } else {
-        tmem_ld_x32(t_s + ch * kColsPer, sr);
-      }
+      uint32_t sr[kSub];
+      tmem_ld_x32(t_s, sr);
+      tmem_ld_x32(t_s + 32, sr + 32);
       tc_wait_ld();
-      const int c0 = i * kSub + ch * kColsPer;  // key index (relative to kv_begin) of this thread's first column
+      const int c0 = i * kSub;  // key index (relative to kv_begin) of the first column
       if (kWin) {
         const int c_lo = w_lo - c0, c_hi = w_hi - c0;  // valid columns: [c_lo, c_hi)
-        if (c_lo > 0 || c_hi < kColsPer) {
+        if (c_lo > 0 || c_hi < kSub) {
 #pragma unroll
-          for (int c = 0; c < kColsPer; ++c)
+          for (int c = 0; c < kSub; ++c)
             if (c < c_lo || c >= c_hi) sr[c] = 0xff800000u;  // -inf
         }
       } else {
         const int valid = w.kv_len - c0;
-        if (valid < kColsPer) {
+        if (valid < kSub) {
 #pragma unroll
-          for (int c = 0; c < kColsPer; ++c)
+          for (int c = 0; c < kSub; ++c)
             if (c >= valid) sr[c] = 0xff800000u;  // -inf
         }
       }
       // row max: independent FMNMX3 chains of 16 columns
-      float mxa[kColsPer / 16];
+      float mxa[kSub / 16];
 #pragma unroll
-      for (int g = 0; g < kColsPer / 16; ++g) {
+      for (int g = 0; g < kSub / 16; ++g) {
         mxa[g] = max3(__uint_as_float(sr[16 * g]), __uint_as_float(sr[16 * g + 1]), __uint_as_float(sr[16 * g + 2]));
 #pragma unroll
         for (int c = 3; c < 15; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[16 * g + c]), __uint_as_float(sr[16 * g + c + 1]));
@@ -350,19 +356,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
       float mx = mxa[0];
 #pragma unroll
-      for (int g = 1; g < kColsPer / 16; ++g) mx = fmaxf(mx, mxa[g]);
-      if constexpr (kColSplit > 1) {
-        // exchange the partial max with the warps sharing these rows (buffer by sub-step parity: one barrier suffices)
-        float* xb = xch + ((i & 1) * 2 + t) * kColSplit * kTileRows;
-        xb[ch * kTileRows + r] = mx;
-        named_bar_sync(bar_id, 32 * kColSplit);
-#pragma unroll
-        for (int o = 0; o < kColSplit; ++o) mx = fmaxf(mx, xb[o * kTileRows + r]);
-      }
+      for (int g = 1; g < kSub / 16; ++g) mx = fmaxf(mx, mxa[g]);
       float alpha = 1.0f;
-      const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first sub-step (m_ref = -inf)
+      const bool grow = mx > m_ref + kRescaleThreshold;  // true on the first sub-step with an unmasked key (m_ref = -inf)
       if (grow) {
-        alpha = ex2(m_ref - mx);  // 0 on the first sub-step
+        alpha = ex2(m_ref - mx);  // 0 when m_ref = -inf
         m_ref = mx;
       }
       // p = 2^(s - m): packed f32x2 subtract and independent packed row-sum accumulators
@@ -371,13 +369,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       if (kPingPong) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");  // the exponents depend on neg_m
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[kColsPer / 2];
+      uint32_t pk[kSub / 2];
 #pragma unroll
-      for (int c = 0; c < kColsPer / 2; ++c) {
+      for (int c = 0; c < kSub / 2; ++c) {
         const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
         uint64_t p2;
         if (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) {
-          p2 = ex2_poly_f32x2(x2);  // FMA/ALU pipes: relieves the MUFU unit, which is the binding pipe at head_dim 80
+          p2 = ex2_poly_f32x2(x2);  // FMA/ALU pipes: relieves the MUFU unit
         } else {
           float x0, x1;
           unpack_f32x2(x2, x0, x1);
@@ -387,6 +385,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         float p0, p1;
         unpack_f32x2(p2, p0, p1);
         pk[c] = pack_bf16(p0, p1);
+        // hand the exponent phase to the other tile's warp once pair kPpAt is through the MUFU unit: the remaining
+        // exponents cover the hand-over latency. The barrier id is made to depend on that pair's result (p >= 0, so the
+        // sign bit adds nothing) because ptxas otherwise hoists the arrive to the top of the phase.
+        if (kPingPong && c == kPpAt && (t == 0 || i + 1 < n_sub)) named_bar_arrive(pp_other + (int)(pk[c] >> 31), 64);
       }
       float sum;
       {
@@ -395,59 +397,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         unpack_f32x2(add_f32x2(acc2[2], acc2[3]), b0, b1);
         sum = (a0 + a1) + (b0 + b1);
       }
-      // hand the exponent phase to the other tile's warp. The barrier id is made to depend on the row sum (>= 0, so the
-      // sign bit adds nothing) because ptxas otherwise hoists the arrive above the exponents it is meant to follow.
-      if (kPingPong && (t == 0 || i + 1 < n_sub)) named_bar_arrive(pp_other + (int)(__float_as_uint(sum) >> 31), 64);
       l = l * alpha + sum;
-      if constexpr (kColsPer == 64) {
-        tmem_st_x16(t_s, pk);
-        tmem_st_x16(t_s + 16, pk + 16);
-      } else {
-        tmem_st_x16(t_s + ch * (kColsPer / 2), pk);
-      }
-      // P.V completions are signalled on two alternating barriers per tile, o_done[t][i&1], so a parity wait stays
-      // unambiguous as long as every completion is observed within two sub-steps. P_{i-2} V (issued two softmaxes ago)
-      // is observed here every sub-step - normally free - and P_{i-1} V only when O really has to be rescaled.
-      if (i > 1) mbar_wait(&o_done[t * 2 + (i & 1)], ((i - 2) >> 1) & 1);
+      tmem_st_x16(t_s, pk);
+      tmem_st_x16(t_s + 16, pk + 16);
+      // P.V completions are signalled on one barrier per S/P buffer, o_done[t][b]; every completion is observed, in
+      // order - P_{i-2} V here, normally long done - so a parity wait stays unambiguous.
+      if (i > 1) mbar_wait(&o_done[t * 2 + b], ph ^ 1);
       if (i > 0) {
-        // O_t holds P V of sub-steps < i relative to the old reference; bring this warp's share of its columns to the
-        // new one before P_i V is added (the warps sharing the rows saw the same max and take the same decision)
+        // O_t holds P V of sub-steps < i relative to the old reference; bring it to the new one before P_i V is added. P_{i-1} V is waited for only when O really has to be rescaled.
         if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&o_done[t * 2 + ((i - 1) & 1)], ((i - 1) >> 1) & 1);
+          mbar_wait(&o_done[t * 2 + (b ^ 1)], ((i - 1) >> 1) & 1);
           tc_fence_after();
-          uint32_t o[kOColsPer];
-          tmem_ld_cols<kOColsPer>(t_o, o);
+          uint32_t o[kHd];
+          tmem_ld_cols<kHd>(t_o, o);
           tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < kOColsPer; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st_cols<kOColsPer>(t_o, o);
+          for (int c = 0; c < kHd; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st_cols<kHd>(t_o, o);
         }
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t * 2 + (i & 1)]);
+      mbar_arrive(&p_full[t * 2 + b]);
     }
-    // ---- epilogue: O / l -> bf16 -> out[row, head*80 + this warp's columns]
-    if constexpr (kColSplit > 1) {
-      float* xb = xch + (((n_sub & 1) * 2) + t) * kColSplit * kTileRows;  // the buffer the last sub-step did not use
-      xb[ch * kTileRows + r] = l;
-      named_bar_sync(bar_id, 32 * kColSplit);
-      l = 0.f;
-#pragma unroll
-      for (int o = 0; o < kColSplit; ++o) l += xb[o * kTileRows + r];
-    }
-    if (n_sub > 1) mbar_wait(&o_done[t * 2 + ((n_sub - 2) & 1)], ((n_sub - 2) >> 1) & 1);
-    mbar_wait(&o_done[t * 2 + ((n_sub - 1) & 1)], ((n_sub - 1) >> 1) & 1);
+    // ---- epilogue: O / l -> bf16 -> out[row, head*80 ...]
+    mbar_wait(&o_done[t * 2 + ((n_sub - 1) & 1)], ((n_sub - 1) >> 1) & 1);  // the last P.V (the pipe completes in order)
     tc_fence_after();
-    uint32_t o[kOColsPer];
-    tmem_ld_cols<kOColsPer>(t_o, o);
+    uint32_t o[kHd];
+    tmem_ld_cols<kHd>(t_o, o);
     tc_wait_ld();
     const float inv = 1.0f / l;
     const int qrow = t * kTileRows + r;
     if (qrow < w.q_rows) {
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(w.q_begin + qrow) * (num_heads * kHd) + head * kHd + ch * kOColsPer);
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(w.q_begin + qrow) * (num_heads * kHd) + head * kHd);
 #pragma unroll
-      for (int c = 0; c < kOColsPer / 8; ++c) {
+      for (int c = 0; c < kHd / 8; ++c) {
         const uint32_t* x = o + c * 8;
         dst[c] = make_uint4(pack_bf16(__uint_as_float(x[0]) * inv, __uint_as_float(x[1]) * inv),
                             pack_bf16(__uint_as_float(x[2]) * inv, __uint_as_float(x[3]) * inv),
@@ -483,9 +467,9 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   }
   dim3 grid((unsigned)n_work, (unsigned)num_heads);
   if (d_win)
-    attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
+    attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
   else
-    attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
+    attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
   KOCR_LAUNCH_CHECK("attention_kernel");
   return KOCR_OK;
 }
