@@ -18,6 +18,7 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -200,8 +201,7 @@ def run_gpu(args):
 
     import torch.distributed as dist
 
-    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, _lib
-    from oracle import vision_oracle as vo  # FLOP formula + seeded weights only (never on the timed path)
+    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, _lib, presets, smart_resize
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,29 +213,20 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = vo.qwen2_5_vl_7b() if args.workload == "c3" else vo.qwen2_vl_7b()
-    tower = KarantaVisionTower(dict(arch=cfg.arch, depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
-                                    mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden, window_size=cfg.window_size,
-                                    fullatt_block_indexes=list(cfg.fullatt_block_indexes)), device=dev)
-    tower.load_state_dict(vo.init_weights(cfg, seed=0))
+    cfg = SimpleNamespace(**presets.preset("qwen2_5_vl_7b" if args.workload == "c3" else "qwen2_vl_7b"))
+    tower = KarantaVisionTower(vars(cfg), device=dev)
+    tower.load_state_dict(presets.random_state_dict(vars(cfg), seed=0))
     enc = PageEncoder(tower, MIN_PIXELS, MAX_PIXELS)
     n_pages = args.pages
     pages = make_pages(n_pages, workload=args.workload)
-    from karanta_ocr_b200 import smart_resize
     grid_ref = []
     for p in pages:
         rh, rw = smart_resize(p.shape[1], p.shape[2], 28, MIN_PIXELS, MAX_PIXELS)
         grid_ref.append([1, rh // 14, rw // 14])
-    flops_step = vo.flops_per_batch(cfg, grid_ref)
+    fl = presets.flops_per_batch(vars(cfg), grid_ref)
+    flops_step = fl["total"]
     N = int(sum(g[1] * g[2] for g in grid_ref))
-    l2_full = float(sum((g[1] * g[2]) ** 2 for g in grid_ref))
-    attn_flops_step = 4.0 * cfg.embed_dim * l2_full * cfg.depth
-    if cfg.arch == "qwen2_5_vl":
-        _, cuw = vo.window_index(np.asarray(grid_ref), cfg.window_size, 2, 14)
-        l2_win = float(((cuw[1:].astype(np.int64) - cuw[:-1]) ** 2).sum())
-        nf = len(cfg.fullatt_block_indexes)
-        attn_flops_step = 4.0 * cfg.embed_dim * (l2_full * nf + l2_win * (cfg.depth - nf))
-    flops_attn_launch = attn_flops_step / cfg.depth
+    flops_attn_launch = fl["attention"] / cfg.depth
 
     # device-resident inputs for `value`; pinned host inputs for `e2e`
     d_pages = [torch.from_numpy(p).to(dev) for p in pages]

@@ -3,7 +3,7 @@
 page image -> smart_resize -> resize/normalise/patchify -> pixel_values + image_grid_thw -> vision tower -> embeddings,
 behind the transformers call surface the reference uses. See DESIGN.md and INTEGRATION.md.
 """
-from . import _lib  # noqa: F401
+from . import _lib, presets  # noqa: F401
 from .image_processor import KarantaImageProcessor, smart_resize  # noqa: F401
 from .llm_handoff import get_rope_index, scatter_image_features  # noqa: F401
 from .pipeline import PageEncoder, gather_pages, page_cost, shard_pages  # noqa: F401

@@ -130,3 +130,22 @@ def test_shard_pages_lpt():
     assert max(loads) - min(loads) <= 3
     assert shard_pages([5] * 64, 8) == [[r + 8 * k for k in range(8)] for r in range(8)]
     assert all(s == sorted(s) for s in shards)
+
+
+@pytest.mark.parametrize("name,ocfg", [("qwen2_vl_7b", vo.qwen2_vl_7b()), ("qwen2_vl_2b", vo.qwen2_vl_2b()), ("qwen2_5_vl_7b", vo.qwen2_5_vl_7b())])
+def test_presets_match_oracle_accounting(name, ocfg):
+    """The product-side presets (what bench.py's GPU arm uses) agree with the oracle's configs, state-dict layout and
+    FLOP formula on uniform and mixed batches."""
+    from karanta_ocr_b200 import presets
+    cfg = presets.preset(name)
+    assert (cfg["arch"], cfg["depth"], cfg["embed_dim"], cfg["num_heads"], cfg["mlp_hidden"], cfg["out_hidden"]) == \
+           (ocfg.arch, ocfg.depth, ocfg.embed_dim, ocfg.num_heads, ocfg.mlp_hidden, ocfg.out_hidden)
+    small = presets.preset(name, depth=2)
+    osmall = vo.TowerConfig(ocfg.arch, 2, ocfg.embed_dim, ocfg.num_heads, ocfg.mlp_hidden, ocfg.out_hidden)
+    a, b = presets.random_state_dict(small, seed=1), vo.init_weights(osmall, seed=1)
+    assert {k: tuple(v.shape) for k, v in a.items()} == {k: tuple(v.shape) for k, v in b.items()}
+    for grid in ([[1, 92, 72]] * 3, [[1, 92, 72], [1, 20, 18], [1, 46, 36], [1, 92, 64]]):
+        got = presets.flops_per_batch(cfg, grid)
+        assert got["total"] == pytest.approx(vo.flops_per_batch(ocfg, grid), rel=1e-12)
+    if name == "qwen2_vl_7b":
+        assert presets.flops_per_batch(cfg, [[1, 92, 72]])["total"] == pytest.approx(15.69e12, rel=2e-3)  # SURVEY.md 8(d)
