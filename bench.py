@@ -52,6 +52,8 @@ WORKLOADS = {
            "in blocks 7/15/23/31), 64 synthetic letter pages u8[3,1288,995] per step per GPU"),
     "c4": ("C4: Qwen2-VL-7B vision tower, mixed-aspect varlen batch of 64 pages per step per GPU drawn (seeded) from "
            "1288x420, 640x880, 256x256, 1288x910, 1288x995, 995x1288"),
+    "c5": ("C5: bulk job of letter pages u8[3,1288,995] (C2's generator) through the Qwen2-VL-7B tower, page-sharded over the GPUs, "
+           "64-page batches, host pages in -> host embeddings out"),
 }
 
 
@@ -359,6 +361,89 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- C5: bulk job, strong scaling
+def run_bulk_job(args):
+    """one job of `--job-pages` letter pages (C2's generator), page-sharded over the ranks with
+    shard_pages (no collective), each rank streaming its shard through PageEncoder.encode_to_host_async in 64-page
+    batches: pinned host pages in, embeddings in pinned host memory out. A step is the whole job; scaling is strong."""
+    import torch.distributed as dist
+
+    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, page_cost, presets, shard_pages
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = presets.preset("qwen2_vl_7b")
+    tower = KarantaVisionTower(cfg, device=dev)
+    tower.load_state_dict(presets.random_state_dict(cfg, seed=0))
+    enc = PageEncoder(tower, MIN_PIXELS, MAX_PIXELS)
+    pool = [torch.from_numpy(p).pin_memory() for p in make_pages(PAGES_PER_STEP)]  # the job cycles over 64 distinct pinned pages
+    total = args.job_pages
+    cost = page_cost(pool[0].shape[1], pool[0].shape[2], MIN_PIXELS, MAX_PIXELS)
+    mine = shard_pages([cost] * total, world)[rank]
+    rows = (92 * 72) // 4
+    outs = [torch.empty((PAGES_PER_STEP * rows, cfg["out_hidden"]), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+
+    def job(indices):
+        pending, k, launches = [], 0, 0
+        for b in range(0, len(indices), PAGES_PER_STEP):
+            batch = [pool[i % len(pool)] for i in indices[b:b + PAGES_PER_STEP]]
+            if len(pending) >= 2:
+                pending.pop(0).synchronize()
+            ev, _, _ = enc.encode_to_host_async(batch, outs[k % 2])
+            launches += enc.last_launch_count
+            pending.append(ev)
+            k += 1
+        for ev in pending:
+            ev.synchronize()
+        return launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        job(mine[:PAGES_PER_STEP])  # warm-up = one batch per rank, not a whole job
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        launches += job(mine)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        value = total * args.steps / (float(ms.item()) / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOADS["c5"], "job_pages": total, "pages_per_rank": len(mine), "batch_pages": PAGES_PER_STEP,
+                           "parallelism": f"page-sharded x{world} (LPT), no collective, host-side results",
+                           "pages": "cycled from a pool of 64 distinct pinned host pages", "weights": "seeded random init"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(sum(pool[i % len(pool)].numel() for i in mine)),
+                        "d2h_bytes_per_step": int(len(mine) * rows * cfg["out_hidden"] * 2)},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "note": "value is measured end to end (host pages in, host embeddings out); there is no device-resident variant of a bulk job"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -367,11 +452,15 @@ def main():
     ap.add_argument("--impl", default="kocr", choices=["kocr", "reference"])
     ap.add_argument("--pages", type=int, default=PAGES_PER_STEP, help="pages per step per GPU (C2 = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
-                    help="c2 = the metric's configuration (default); c3 / c4 = the other BASELINE.json configs, for the record")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = the metric's configuration (default); c3 / c4 = the other BASELINE.json configs, for the record; "
+                         "c5 = one bulk job of --job-pages pages sharded over the ranks (strong scaling)")
+    ap.add_argument("--job-pages", type=int, default=8192, help="c5 only: pages in the whole job")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_bulk_job(args)
     else:
         run_gpu(args)
 
