@@ -33,18 +33,28 @@ static constexpr int kTileRows = 128;
 static constexpr int kSub = 64;              // keys per score sub-step (S and P are double-buffered per query tile)
 static constexpr int kChunkBytes = kTileRows * 32;  // 4096
 static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
-static constexpr int kKvStages = 3;
+// Two kernel shapes. Full attention (long key ranges): two query tiles per CTA, 384 threads, all 512 TMEM columns, three
+// K/V stages, one CTA per SM. Windowed layers (a 128-row block needs at most ~190 keys, three sub-steps): one query tile
+// per CTA, 256 threads, 256 TMEM columns, two K/V stages, so that two CTAs share an SM and the prologue / epilogue of
+// one overlaps the few sub-steps of the other; each tile also gets its own, tight key range.
+template <bool kWin> struct AttnShape {
+  static constexpr int kTiles = kWin ? 1 : 2;
+  static constexpr int kStages = kWin ? 2 : 3;
+  static constexpr int kThreads = 128 + 128 * kTiles;
+  static constexpr int kTmemCols = kWin ? 256 : 512;
+  static constexpr int kSmem = 2 * kStages * kTileBytes + 512 + 1024;
+  static constexpr int kProdRegs = kWin ? 56 : 96;  // TMA / MMA warps; softmax warps take 200: 128*56 + 128*200 = 256*128, 128*96 + 256*200 <= 384*168
+  __host__ __device__ static constexpr int o_col(int t) { return kWin ? 128 : 256 + t * 128; }  // O_t; S[t][b] is at t*128 + b*64
+  __host__ __device__ static constexpr int q_col(int t) { return o_col(t) + kHd; }               // Q_t right behind O_t
+};
 #ifndef KOCR_PINGPONG
 #define KOCR_PINGPONG 1
 #endif
 static constexpr bool kPingPong = KOCR_PINGPONG;
-static constexpr int kAttnThreads = 384;
-static constexpr int kQCol = 256 + kHd;                    // TMEM column of Q_t within tile t's 128-column half (behind O_t)
 #ifndef KOCR_PP_AT
 #define KOCR_PP_AT 22
 #endif
 static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over after this pair of columns (of 32; must be a MUFU pair)
-static constexpr int kAttnSmem = 2 * kKvStages * kTileBytes + 512 + 1024;
 #ifndef KOCR_POLY_EVERY
 #define KOCR_POLY_EVERY 4
 #endif
@@ -139,9 +149,13 @@ __device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
 // kWin: block-diagonal attention inside a query block (Qwen2.5-VL windows, HF modeling_qwen2_5_vl.py:498-502): row r may
 // attend only the keys [win[r].x, win[r].y) of its own window; a 256-row block packs four or more windows.
 template <bool kWin>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(AttnShape<kWin>::kThreads, kWin ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                  const AttnWork* __restrict__ work, int num_heads, const int2* __restrict__ win) {
+  using Shape = AttnShape<kWin>;
+  constexpr int kTiles = Shape::kTiles;
+  constexpr int kKvStages = Shape::kStages;
+  constexpr bool kPP = kPingPong && kTiles == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_k = smem;                                   // kKvStages tiles
@@ -172,9 +186,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
     mbar_init(q_full1, 128);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 2);  // one tcgen05.commit from each query tile's MMA warp
+      mbar_init(&k_empty[s], kTiles);  // one tcgen05.commit from each query tile's MMA warp
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 2);
+      mbar_init(&v_empty[s], kTiles);
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(&s_full[t], 1);
@@ -183,7 +197,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<Shape::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,7 +206,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
   // first 32 columns of S[t][b]; O[t] (80 columns) at 256 + t*128.
 
   if (warp < 4) {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<Shape::kProdRegs>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane issues)
       const int kv_begin = (int)uniform_u32(w.kv_begin);
@@ -216,7 +230,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
         }
         __syncwarp();
       }
-    } else if (warp == 1 || warp == 2) {
+    } else if (warp == 1 || (warp == 2 && kTiles == 2)) {
       // ---------------------------------------------------------------- MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
       // (warp-uniform loops, elected lane issues). Scores are double-buffered per query tile: S_t(i+2) is issued right
       // after P_t(i).V, two sub-steps ahead of the softmax that will read it, so the softmax warps do not wait for the
@@ -227,10 +241,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
       const int t = warp - 1;
       const uint32_t tmem_u = uniform_u32(tmem_base);
       const int n_sub_u = (int)uniform_u32(n_sub);
-      const uint32_t q_tm = tmem_u + kQCol + t * 128;  // Q_t as the A operand in TMEM (bf16 pairs, 8 columns per 16 dims)
+      const uint32_t q_tm = tmem_u + Shape::q_col(t);  // Q_t as the A operand in TMEM (bf16 pairs, 8 columns per 16 dims)
       const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
       const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kChunkBytes);  // LBO = distance between 16-column groups
-      const uint32_t d_o = tmem_u + 256 + t * 128;
+      const uint32_t d_o = tmem_u + Shape::o_col(t);
       auto issue_s = [&](int i) {
         const int s = (i >> 1) % kKvStages;
         const uint32_t ka = k_lo + s * (kTileBytes >> 4) + (i & 1) * ((kSub * 32) >> 4);
@@ -276,18 +290,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
     }
   } else {
     // ------------------------------------------------------------------ softmax warps, one query row per thread
-    setmaxnreg_inc<200>();                   // 128*96 + 256*200 <= 384*168 (the launch allocation)
+    setmaxnreg_inc<200>();                   // see AttnShape::kProdRegs for the budget
     const int sw = warp - 4;
     const int t = sw >> 2;                   // query tile
     const int qtr = warp & 3;                // TMEM lane quarter
     const int r = qtr * 32 + lane;           // row within the tile
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    const uint32_t t_o = tmem_base + 256 + t * 128 + lane_off;
+    const uint32_t t_o = tmem_base + Shape::o_col(t) + lane_off;
     // Exponent phase hand-over (kPingPong): the two tiles' warps of one lane quarter sit on the same scheduler and share
     // its MUFU unit. Left alone they run in lockstep - both in the exponent phase, then both in the TMEM / max / pack
     // phase - and the unit idles half the time. A token passed through two 64-thread named barriers makes them alternate.
     const int pp_mine = 1 + t * 4 + qtr, pp_other = 1 + (1 - t) * 4 + qtr;
-    if (kPingPong && t == 1) named_bar_arrive(pp_other, 64);  // tile 0 goes first
+    if (kPP && t == 1) named_bar_arrive(pp_other, 64);  // tile 0 goes first
     {
       // this thread's query row -> TMEM, as the A operand of S = Q K^T: Q is then read from shared memory by no MMA
       // (a 128 x 64 x 16 MMA with both operands in shared memory is bound by its 6 KB of operand reads, not by the math)
@@ -304,7 +318,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
 #pragma unroll
         for (int c = 0; c < kHd / 2; ++c) qw[c] = 0u;
       }
-      tmem_st_cols<kHd / 2>(tmem_base + kQCol + t * 128 + lane_off, qw);
+      tmem_st_cols<kHd / 2>(tmem_base + Shape::q_col(t) + lane_off, qw);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(t == 0 ? q_full : q_full1);
@@ -366,7 +380,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
       // p = 2^(s - m): packed f32x2 subtract and independent packed row-sum accumulators
       // (a row whose keys so far are all masked still has m_ref = -inf: subtract 0 so its p are 2^-inf = 0, not NaN)
       float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-      if (kPingPong) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");  // the exponents depend on neg_m
+      if (kPP) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");  // the exponents depend on neg_m
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[kSub / 2];
@@ -388,7 +402,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
         // hand the exponent phase to the other tile's warp once pair kPpAt is through the MUFU unit: the remaining
         // exponents cover the hand-over latency. The barrier id is made to depend on that pair's result (p >= 0, so the
         // sign bit adds nothing) because ptxas otherwise hoists the arrive to the top of the phase.
-        if (kPingPong && c == kPpAt && (t == 0 || i + 1 < n_sub)) named_bar_arrive(pp_other + (int)(pk[c] >> 31), 64);
+        if (kPP && c == kPpAt && (t == 0 || i + 1 < n_sub)) named_bar_arrive(pp_other + (int)(pk[c] >> 31), 64);
       }
       float sum;
       {
@@ -445,7 +459,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Shape::kTmemCols>(tmem_base);
   }
 }
 
@@ -461,15 +475,15 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   if (rc) return rc;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnShape<false>::kSmem));
+    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnShape<true>::kSmem));
     attr_set = true;
   }
   dim3 grid((unsigned)n_work, (unsigned)num_heads);
   if (d_win)
-    attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
+    attention_kernel<true><<<grid, AttnShape<true>::kThreads, AttnShape<true>::kSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
   else
-    attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
+    attention_kernel<false><<<grid, AttnShape<false>::kThreads, AttnShape<false>::kSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
   KOCR_LAUNCH_CHECK("attention_kernel");
   return KOCR_OK;
 }
@@ -501,8 +515,8 @@ int build_attn_work_windowed(const int32_t* cu, int n_seqs, const int32_t* cu_wi
   }
   for (int i = 0; i < n_seqs; ++i) {
     const int b = cu[i], e = cu[i + 1];
-    for (int q = b; q < e; q += 2 * kTileRows) {
-      const int rows = std::min(2 * kTileRows, e - q);
+    for (int q = b; q < e; q += kTileRows) {  // one query tile per CTA on windowed layers (AttnShape<true>)
+      const int rows = std::min(kTileRows, e - q);
       const int kv0 = (*row_win)[2 * (size_t)q], kv1 = (*row_win)[2 * (size_t)(q + rows - 1) + 1];
       out->push_back(AttnWork{q, rows, kv0, kv1 - kv0});
     }

@@ -58,7 +58,7 @@ def test_preprocess_uses_bulk_store(sass):
 
 
 def test_attention_exponent_phase_is_between_the_hand_over_barriers(sass):
-    for body in _of(sass, "attention_kernel"):
+    for body in _of(sass, "attention_kernelILb0"):  # the two-tile (full attention) shape; windowed CTAs hold one tile
         sync = [i for i, op in enumerate(body) if re.match(r"BAR\.SYNC\S* R\d+, 0x40", op)]
         arv = [i for i, op in enumerate(body) if re.match(r"(@!?P\d+ )?BAR\.ARV R\d+, 0x40", op)]
         assert len(sync) == 1 and len(arv) == 2, (sync, arv)  # wait for the token; initial hand-over + per-sub-step hand-over

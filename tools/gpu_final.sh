@@ -18,5 +18,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_kernel|
 echo "ncu launches exit $?"
 # full counters, one launch of each hot kernel at the C2 batch size (64 pages, depth 1)
 python tools/prof_target.py 64 > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"attention_kernel|preprocess_kernel|gemm_kernel|norm_kernel" -s 11 -c 11 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"attention_kernel|preprocess_kernel|gemm_kernel|norm_kernel" -c 24 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
 echo "ncu full exit $?"

@@ -2,14 +2,13 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from karanta_ocr_b200 import KarantaVisionTower, PageEncoder
-from oracle import vision_oracle as vo
+from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, presets
 from tests.synth import synth_page
 
 n_pages = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-cfg = vo.qwen2_vl_7b(depth=1)
-tower = KarantaVisionTower(dict(arch="qwen2_vl", depth=1, embed_dim=1280, num_heads=16, mlp_hidden=5120, out_hidden=3584))
-tower.load_state_dict(vo.init_weights(cfg, seed=0))
+cfg = presets.preset("qwen2_vl_7b", depth=1)
+tower = KarantaVisionTower(cfg)
+tower.load_state_dict(presets.random_state_dict(cfg, seed=0))
 enc = PageEncoder(tower)
 pages = [torch.from_numpy(synth_page(1288, 995, 1234 + i)).cuda() for i in range(n_pages)]
 for _ in range(2):

@@ -1,0 +1,119 @@
+"""Turn the ncu outputs of tools/gpu_final.sh into the tracked summaries under profiles/:
+  launches csv (gpu__time_duration per launch of the bench command)  -> r1_ncu_launch_summary_bench_pages8.csv
+  full report (.ncu-rep, one prof_target.py run at the C2 batch size) -> r1_ncu_full_kernels_pages64.csv, r1_traffic.json
+Usage: python tools/summarize_ncu.py gpurun_out/launches_final.csv gpurun_out/prof_final.ncu-rep"""
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(ROOT, "profiles")
+NCU = "/usr/local/cuda/bin/ncu"
+
+# kernel (template arguments included) -> bench.py profile class, for the depth-1 Qwen2-VL target
+def classify(name, seen):
+    if "attention_kernel" in name:
+        return "attention"
+    if "preprocess_kernel" in name:
+        return "preprocess"
+    if "norm_kernel" in name and "fold" not in name:
+        return "norm_merger"
+    m = re.search(r"gemm_kernel<(\d+), (\d+)>", name)
+    if not m:
+        return None
+    bn, epi = int(m.group(1)), int(m.group(2))
+    if epi == 100:
+        return "gemm_qkv_rope"
+    if epi == 2:
+        return "gemm_fc1"
+    if epi == 3:
+        return "gemm_merger_fc1"
+    if epi == 1:
+        return "gemm_merger_fc2"
+    if epi == 0:
+        return "gemm_patch_embed"
+    if epi == 4:  # bias + residual: proj first, fc2 second within a block
+        seen["res"] = seen.get("res", 0) + 1
+        return "gemm_proj" if seen["res"] % 2 == 1 else "gemm_fc2"
+    return f"gemm_{bn}_{epi}"
+
+
+def short(name):
+    name = re.sub(r"^void (kocr::)?", "", name)
+    return re.sub(r"\(.*", "", name)
+
+
+def launch_summary(path):
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    ui = hdr.index("Metric Unit")
+    agg = OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v_ms = v / 1e6 if r[ui] in ("ns", "nsecond") else v / 1e3 if r[ui] in ("us", "usecond") else v
+        a = agg.setdefault(short(r[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += v_ms
+    total = sum(a[1] for a in agg.values())
+    out = os.path.join(PROF, "r1_ncu_launch_summary_bench_pages8.csv")
+    with open(out, "w") as f:
+        f.write("kernel,launches,total_ms,share_pct,avg_us\n")
+        for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k},{n},{ms:.3f},{100 * ms / total:.2f},{1e3 * ms / n:.1f}\n")
+    print("wrote", out)
+
+
+COLS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_active.avg", "sm__cycles_elapsed.avg.per_second"]
+
+
+def full_summary(rep):
+    raw = subprocess.run([NCU, "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ci = {h: i for i, h in enumerate(hdr)}
+    seen, last = {}, OrderedDict()
+    for r in data:  # the target encodes twice; the second (warm) launch of each kernel overwrites the first
+        cls = classify(r[ci["Kernel Name"]], seen)
+        if cls:
+            last[cls] = r
+    out = os.path.join(PROF, "r1_ncu_full_kernels_pages64.csv")
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["class", "Kernel Name", "Grid Size", "Block Size"] + [f"{c} [{units[ci[c]]}]" for c in COLS])
+        for cls, r in last.items():
+            w.writerow([cls, short(r[ci["Kernel Name"]]), r[ci["Grid Size"]], r[ci["Block Size"]]] + [r[ci[c]] for c in COLS])
+    print("wrote", out)
+
+    def to_bytes(r, c):
+        v, u = float(r[ci[c]].replace(",", "")), units[ci[c]].lower()
+        return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}[u]
+
+    def to_ms(r):
+        v, u = float(r[ci["gpu__time_duration.sum"]].replace(",", "")), units[ci["gpu__time_duration.sum"]].lower()
+        return v * {"ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}[u]
+    tj = {"source": "ncu --set full --clock-control none, tools/prof_target.py 64 (C2 batch: 64 letter pages, Qwen2-VL-7B widths, depth 1), "
+                    "warm launch of each kernel; profiles/r1_ncu_full_kernels_pages64.csv",
+          "dram_bytes_per_launch": {k: int(to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) for k, r in last.items()},
+          "ncu_ms_per_launch": {k: to_ms(r) for k, r in last.items()}}
+    out = os.path.join(PROF, "r1_traffic.json")
+    json.dump(tj, open(out, "w"), indent=1)
+    print("wrote", out)
+    for k, r in last.items():
+        print(f"{k:18s} {to_ms(r):8.3f} ms  dram {tj['dram_bytes_per_launch'][k] / 1e9:6.2f} GB  tensor {r[ci[COLS[4]]]:>6s}%  xu {r[ci[COLS[5]]]:>6s}%  issue {r[ci[COLS[6]]]:>6s}%")
+
+
+if __name__ == "__main__":
+    launch_summary(sys.argv[1])
+    if len(sys.argv) > 2:
+        full_summary(sys.argv[2])
