@@ -61,10 +61,10 @@ def _as_u8_page(image):
     (inside the kernel), alpha is dropped."""
     if hasattr(image, "convert") and hasattr(image, "mode"):  # PIL
         if image.mode == "L":
-            a = np.asarray(image)
-            return torch.from_numpy(np.ascontiguousarray(a)), a.shape[0], a.shape[1], _lib.LAYOUT_GRAY
-        a = np.asarray(image.convert("RGB"))
-        return torch.from_numpy(np.ascontiguousarray(a)), a.shape[0], a.shape[1], _lib.LAYOUT_HWC
+            a = np.array(image)  # a writable copy: torch refuses to wrap PIL's read-only buffer without a warning
+            return torch.from_numpy(a), a.shape[0], a.shape[1], _lib.LAYOUT_GRAY
+        a = np.array(image.convert("RGB"))
+        return torch.from_numpy(a), a.shape[0], a.shape[1], _lib.LAYOUT_HWC
     t = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(image)))
     if t.dtype != torch.uint8:
         raise ValueError(f"page images must be uint8 (got {t.dtype}); rescale before the processor is not supported")

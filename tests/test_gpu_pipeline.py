@@ -43,3 +43,32 @@ def test_sharded_encode_single_rank_order():
     for i, p in enumerate(pages):
         one, _ = enc.encode([p])
         assert torch.equal(ordered[i], one.cpu())
+
+
+def test_bulk_encode_job_over_reference_jsonl(tmp_path):
+    """SURVEY.md section 8 row f4 on the GPU: request JSONL in the reference's schema (RGB and grayscale PNG data-URIs) ->
+    result files; each page's stored embedding equals encoding that page on its own."""
+    import json
+
+    import numpy as np
+    from PIL import Image
+
+    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, bulk
+    from tests.test_bulk_formats import make_requests
+    cfg = vo.TowerConfig("qwen2_vl", 1, 160, 2, 640, 256)
+    tower = KarantaVisionTower(dict(arch="qwen2_vl", depth=1, embed_dim=160, num_heads=2, mlp_hidden=640, out_hidden=256))
+    tower.load_state_dict(vo.init_weights(cfg, seed=4))
+    enc = PageEncoder(tower)
+    pages = [synth_page(140, 112, 1), synth_page(84, 196, 2), synth_page(56, 56, 3), synth_page(280, 280, 4), synth_page(112, 140, 5)]
+    path = make_requests(tmp_path, pages, gray={1, 4})
+    s = bulk.run_encode_job(path, str(tmp_path / "job"), enc, batch_pages=2)
+    assert s["completed"] == 5 and s["failed"] == 0
+    for i, p in enumerate(pages):
+        tid = f"doc{i}.pdf-{i + 1}"
+        img = Image.fromarray(np.transpose(p, (1, 2, 0)))
+        if i in (1, 4):
+            img = img.convert("L")
+        one, grid = enc.encode([img])
+        rec = json.load(open(tmp_path / "job" / "results" / f"{tid}.json"))
+        assert rec["result"]["image_grid_thw"] == grid.tolist()[0]
+        assert torch.equal(bulk.load_embedding(str(tmp_path / "job"), tid), one.cpu())
