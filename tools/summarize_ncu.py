@@ -1,7 +1,7 @@
 """Turn the ncu outputs of tools/gpu_final.sh into the tracked summaries under profiles/:
   launches csv (gpu__time_duration per launch of the bench command)  -> r1_ncu_launch_summary_bench_pages8.csv
   full report (.ncu-rep, one prof_target.py run at the C2 batch size) -> r1_ncu_full_kernels_pages64.csv, r1_traffic.json
-Usage: python tools/summarize_ncu.py gpurun_out/launches_final.csv gpurun_out/prof_final.ncu-rep"""
+Usage: python tools/summarize_ncu.py gpurun_out/launches_final.csv gpurun_out/prof_final_raw.csv   (or the .ncu-rep)"""
 import csv
 import io
 import json
@@ -78,7 +78,8 @@ COLS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full_summary(rep):
-    raw = subprocess.run([NCU, "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run([NCU, "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ci = {h: i for i, h in enumerate(hdr)}
