@@ -133,3 +133,23 @@ def test_attention_key_order():
 def test_attention_random(cu, heads):
     out, ref = _attn_case(cu, heads, 30)
     _close(out, ref, 2e-2)
+
+
+def test_attention_longest_sequence():
+    """The longest sequence the path can produce: max_pixels = 12 845 056 caps one image at 65 536 patches (e.g. a
+    3584 x 3584 page), i.e. 1024 score sub-steps per query block. The fp32 reference would need a 17 GB score matrix per
+    head, so this compares against torch's flash SDPA in bf16 on the same device (an independent implementation), plus the
+    exact property that identical keys give the mean of V."""
+    S, H = 65536, 2
+    g = torch.Generator().manual_seed(77)
+    q, k, v = (torch.randn(S, H, 80, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+    out = gu.op_attention(gu.pack_qkv(q, k, v), [0, S], H).float().reshape(S, H, 80)
+    with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.FLASH_ATTENTION):
+        ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None])
+    ref = ref[0].transpose(0, 1).float()
+    err = ((out - ref).abs().max() / ref.abs().max()).item()
+    assert err <= 3e-2, err  # two bf16 flash implementations against each other
+    kc = k[:1].expand(S, H, 80).contiguous()
+    out2 = gu.op_attention(gu.pack_qkv(q, kc, v), [0, S], H).float().reshape(S, H, 80)
+    mean_v = v.float().mean(0, keepdim=True).expand(S, H, 80)
+    assert ((out2 - mean_v).abs().max() / mean_v.abs().max()).item() <= 2e-2

@@ -119,3 +119,16 @@ def test_full_batch_idempotent_and_page_independent():
     for i in (0, 5, 63):
         one, _ = p.preprocess_device([pages[i % 8]], torch.float32)
         assert torch.equal(batch[i * 6624:(i + 1) * 6624], one)
+
+
+@pytest.mark.parametrize("backend,shape", [("torchvision", (4200, 4100)), ("pil", (3700, 3650))])
+def test_largest_page_vs_oracle(backend, shape):
+    """A page above max_pixels: resized down to the largest grid the path can produce (~65 536 patches, the longest
+    filter supports and the widest row tables), still bit-exact."""
+    rng = np.random.default_rng(5)
+    page = rng.integers(0, 256, (3,) + shape, dtype=np.uint8)
+    out = _proc(backend)(images=[page])
+    ref_pv, ref_grid = po.preprocess([page], 3136, CKPT_MAX, MODES[backend])
+    g = out["image_grid_thw"].numpy()
+    assert np.array_equal(g, ref_grid) and 60000 < int(g[0, 1] * g[0, 2]) <= 65536
+    assert np.array_equal(out["pixel_values"].numpy(), ref_pv)
