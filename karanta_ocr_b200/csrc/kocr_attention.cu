@@ -12,11 +12,12 @@
 //   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (Q from TMEM) and O_t += P_t V (P from TMEM, V MN-major)
 //   warps 4-7   softmax of query tile 0 (rows 0..127), one row per thread
 //   warps 8-11  softmax of query tile 1 (rows 128..255)
-// Operand tiles are stored as five [128 rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
-// Q/K (K = head_dim) and, unchanged, a canonical MN-major layout for V (N = head_dim): no transpose, no padding of 80.
+// K/V tiles are stored as five [128 rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
+// K (K = head_dim) and, unchanged, a canonical MN-major layout for V (N = head_dim): no transpose, no padding of 80.
 // Scores are produced in 64-key sub-steps and double-buffered in TMEM per query tile (S[t][b], b = sub-step parity), so
-// S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe and the
-// kernel runs at the MUFU (ex2) rate, which is the binding unit for head_dim 80.
+// S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe. What
+// bounds the kernel is the softmax warps' own serial chain per sub-step (TMEM load, row max, 64 exponentials at the
+// MUFU rate, pack, TMEM store, barrier round trips); the two tiles' warps take turns on the MUFU unit (kPingPong).
 // TMEM: S[t][b] at t*128 + b*64 (64 columns); P[t][b] (bf16) overwrites the first 32 columns of S[t][b]; O_t at 256 + t*128;
 // Q_t (bf16 pairs, 40 columns, written once by the softmax threads from global memory) at 336 + t*128.
 #include <algorithm>
@@ -57,9 +58,6 @@ static constexpr bool kPingPong = KOCR_PINGPONG;
 static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over after this pair of columns (of 32; must be a MUFU pair)
 #ifndef KOCR_POLY_EVERY
 #define KOCR_POLY_EVERY 4
-#endif
-#ifndef KOCR_PREFETCH_S
-#define KOCR_PREFETCH_S 0
 #endif
 static constexpr int kPolyEvery = KOCR_POLY_EVERY;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the row max grows by more than 2^8
