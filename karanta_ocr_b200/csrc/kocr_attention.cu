@@ -8,18 +8,19 @@
 // rotated and multiplied by head_dim^-0.5 * log2(e) (fused QKV GEMM epilogue), so scores are in the log2 domain.
 //
 // CTA = one 256-row query block of one sequence and one head; 384 threads:
-//   warp 0      TMA producer: a ring of K tiles and a ring of V tiles (128 keys each)
-//   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (Q from TMEM) and O_t += P_t V (P from TMEM, V MN-major)
+//   warp 0      TMA producer: Q once, then a ring of K tiles and a ring of V tiles (80 keys each = one score sub-step)
+//   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (SS) and O_t += P_t V (P from TMEM, V MN-major)
 //   warps 4-7   softmax of query tile 0 (rows 0..127), one row per thread
 //   warps 8-11  softmax of query tile 1 (rows 128..255)
-// K/V tiles are stored as five [128 rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
-// K (K = head_dim) and, unchanged, a canonical MN-major layout for V (N = head_dim): no transpose, no padding of 80.
-// Scores are produced in 64-key sub-steps and double-buffered in TMEM per query tile (S[t][b], b = sub-step parity), so
-// S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe. What
-// bounds the kernel is the softmax warps' own serial chain per sub-step (TMEM load, row max, 64 exponentials at the
-// MUFU rate, pack, TMEM store, barrier round trips); the two tiles' warps take turns on the MUFU unit (kPingPong).
-// TMEM: S[t][b] at t*128 + b*64 (64 columns); P[t][b] (bf16) overwrites the first 32 columns of S[t][b]; O_t at 256 + t*128;
-// Q_t (bf16 pairs, 40 columns, written once by the softmax threads from global memory) at 336 + t*128.
+// Operand tiles are stored as five [rows x 16 columns] SWIZZLE_32B chunks, which is a canonical K-major layout for
+// Q/K (K = head_dim) and, unchanged, a canonical MN-major layout for V (N = head_dim): no transpose, no padding of 80.
+// Scores are produced in 80-key sub-steps and double-buffered in TMEM per query tile (S[t][b], b = sub-step parity), so
+// S_t(i+2) is computed while the softmax warps still work on sub-step i: they never wait for the tensor pipe. 80 is
+// the largest sub-step for which two tiles x two score buffers and the two O accumulators fit the 512 TMEM columns
+// (4*80 + 2*80 = 480). What bounds the kernel is the softmax warps' own serial chain per sub-step (TMEM load, row max,
+// 80 exponentials, pack, TMEM store, barrier round trips); the two tiles' warps take turns on the MUFU unit (kPingPong).
+// TMEM: S[t][b] at t*160 + b*80 (80 columns); P[t][b] (bf16) overwrites the first 40 columns of S[t][b]; O_t at 320 + t*80
+// (windowed shape: 64-key sub-steps, S[b] at b*64, O at 128).
 #include <algorithm>
 #include <vector>
 
@@ -31,31 +32,35 @@ namespace kocr {
 static constexpr int kHd = 80;
 static constexpr int kChunks = kHd / 16;           // 5 chunks of 16 columns
 static constexpr int kTileRows = 128;
-static constexpr int kSub = 64;              // keys per score sub-step (S and P are double-buffered per query tile)
-static constexpr int kChunkBytes = kTileRows * 32;  // 4096
-static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480
-// Two kernel shapes. Full attention (long key ranges): two query tiles per CTA, 384 threads, all 512 TMEM columns, three
+static constexpr int kChunkBytes = kTileRows * 32;  // 4096 (Q)
+static constexpr int kTileBytes = kChunks * kChunkBytes;  // 20480 (Q)
+// Two kernel shapes. Full attention (long key ranges): two query tiles per CTA, 384 threads, all 512 TMEM columns, six
 // K/V stages, one CTA per SM. Windowed layers (a 128-row block needs at most ~190 keys, three sub-steps): one query tile
-// per CTA, 256 threads, 256 TMEM columns, two K/V stages, so that two CTAs share an SM and the prologue / epilogue of
-// one overlaps the few sub-steps of the other; each tile also gets its own, tight key range.
+// per CTA, 256 threads, 256 TMEM columns, three K/V stages (97 KB), so that two CTAs share an SM and the prologue /
+// epilogue of one overlaps the few sub-steps of the other; each tile also gets its own, tight key range.
 template <bool kWin> struct AttnShape {
+  // keys per score sub-step = keys per K/V tile. Full attention: 80, the largest for which two tiles x two score buffers
+  // and two O accumulators fit the 512 TMEM columns. Windowed: 64 (a block's ~190 keys are three sub-steps either way).
+  static constexpr int kSub = kWin ? 64 : 80;
+  static constexpr int kKvChunkBytes = kSub * 32;               // 2560 / 2048
+  static constexpr int kKvTileBytes = kChunks * kKvChunkBytes;  // 12800 / 10240
   static constexpr int kTiles = kWin ? 1 : 2;
-  static constexpr int kStages = kWin ? 2 : 3;
+  static constexpr int kStages = kWin ? 3 : 6;
   static constexpr int kThreads = 128 + 128 * kTiles;
   static constexpr int kTmemCols = kWin ? 256 : 512;
-  static constexpr int kSmem = 2 * kStages * kTileBytes + 512 + 1024;
+  static constexpr int kSmem = kTiles * kTileBytes + 2 * kStages * kKvTileBytes + 512 + 1024;
   static constexpr int kProdRegs = kWin ? 56 : 96;  // TMA / MMA warps; softmax warps take 200: 128*56 + 128*200 = 256*128, 128*96 + 256*200 <= 384*168
-  __host__ __device__ static constexpr int o_col(int t) { return kWin ? 128 : 256 + t * 128; }  // O_t; S[t][b] is at t*128 + b*64
-  __host__ __device__ static constexpr int q_col(int t) { return o_col(t) + kHd; }               // Q_t right behind O_t
+  __host__ __device__ static constexpr int s_col(int t, int b) { return t * 2 * kSub + b * kSub; }     // S[t][b] (P[t][b] in its first half)
+  __host__ __device__ static constexpr int o_col(int t) { return (kWin ? 2 : 4) * kSub + t * kHd; }   // O_t behind the score buffers
 };
 #ifndef KOCR_PINGPONG
 #define KOCR_PINGPONG 1
 #endif
 static constexpr bool kPingPong = KOCR_PINGPONG;
 #ifndef KOCR_PP_AT
-#define KOCR_PP_AT 22
+#define KOCR_PP_AT 28
 #endif
-static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over after this pair of columns (of 32; must be a MUFU pair)
+static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over after this pair of columns (of 40; must be a MUFU pair)
 #ifndef KOCR_POLY_EVERY
 #define KOCR_POLY_EVERY 4
 #endif
@@ -148,18 +153,20 @@ __device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
 // attend only the keys [win[r].x, win[r].y) of its own window; a 256-row block packs four or more windows.
 template <bool kWin>
 __global__ void __launch_bounds__(AttnShape<kWin>::kThreads, kWin ? 2 : 1)
-attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, __nv_bfloat16* __restrict__ out,
                  const AttnWork* __restrict__ work, int num_heads, const int2* __restrict__ win) {
   using Shape = AttnShape<kWin>;
   constexpr int kTiles = Shape::kTiles;
   constexpr int kKvStages = Shape::kStages;
+  constexpr int kSub = Shape::kSub, kKvChunkBytes = Shape::kKvChunkBytes, kKvTileBytes = Shape::kKvTileBytes;
   constexpr bool kPP = kPingPong && kTiles == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_k = smem;                                   // kKvStages tiles
-  uint8_t* smem_v = smem_k + kKvStages * kTileBytes;        // kKvStages tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKvStages * kTileBytes);
-  uint64_t* q_full = bars;                 // 1 (query tile 0; tile 1's is behind the tmem slot)
+  uint8_t* smem_q = smem;                                   // kTiles query tiles
+  uint8_t* smem_k = smem_q + kTiles * kTileBytes;           // kKvStages tiles of kSub keys
+  uint8_t* smem_v = smem_k + kKvStages * kKvTileBytes;      // kKvStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKvStages * kKvTileBytes);
+  uint64_t* q_full = bars;                 // 1
   uint64_t* k_full = bars + 1;             // kKvStages
   uint64_t* k_empty = k_full + kKvStages;  // kKvStages
   uint64_t* v_full = k_empty + kKvStages;
@@ -168,20 +175,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
   uint64_t* p_full = s_full + 4;           // [tile][buffer] = 4
   uint64_t* o_done = p_full + 4;           // [tile][sub-step parity] = 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
-  uint64_t* q_full1 = o_done + 5;
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const AttnWork w = work[blockIdx.x];
   const int head = blockIdx.y;
-  const int n_kv = (w.kv_len + kTileRows - 1) / kTileRows;  // 128-key smem tiles
-  const int n_sub = (w.kv_len + kSub - 1) / kSub;           // 64-key score sub-steps
+  const int n_sub = (w.kv_len + kSub - 1) / kSub;           // score sub-steps = K/V tiles
   const int col_q = head * 3 * kHd, col_k = col_q + kHd, col_v = col_q + 2 * kHd;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    mbar_init(q_full, 128);   // the 128 softmax threads of a tile each put their query row into TMEM
-    mbar_init(q_full1, 128);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    mbar_init(q_full, 1);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], kTiles);  // one tcgen05.commit from each query tile's MMA warp
@@ -200,31 +205,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S[t][b] (64 f32 columns, b = sub-step parity) at t*128 + b*64; P[t][b] (bf16 pairs) overwrites the
-  // first 32 columns of S[t][b]; O[t] (80 columns) at 256 + t*128.
+  // TMEM columns: S[t][b] (80 f32 columns, b = sub-step parity) at t*160 + b*80; P[t][b] (bf16 pairs) overwrites the
+  // first 40 columns of S[t][b]; O[t] (80 columns) behind the score buffers.
 
   if (warp < 4) {
     setmaxnreg_dec<Shape::kProdRegs>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (warp-uniform, elected lane issues)
-      const int kv_begin = (int)uniform_u32(w.kv_begin);
-      const int n_kv_u = (int)uniform_u32(n_kv);
-      for (int j = 0; j < n_kv_u; ++j) {
+      const int kv_begin = (int)uniform_u32(w.kv_begin), q_begin = (int)uniform_u32(w.q_begin);
+      const int n_sub_u = (int)uniform_u32(n_sub);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, kTiles * kTileBytes);
+        for (int t = 0; t < kTiles; ++t)
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_q, q_full, col_q + c * 16, q_begin + t * kTileRows);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_sub_u; ++j) {
         const int s = j % kKvStages;
         const uint32_t ph = (j / kKvStages) & 1;
-        const int row = kv_begin + j * kTileRows;
+        const int row = kv_begin + j * kSub;
         mbar_wait(&k_empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&k_full[s], kTileBytes);
+          mbar_expect_tx(&k_full[s], kKvTileBytes);
           for (int c = 0; c < kChunks; ++c)
-            tma_load_2d(smem_k + s * kTileBytes + c * kChunkBytes, &tm_qkv, &k_full[s], col_k + c * 16, row);
+            tma_load_2d(smem_k + s * kKvTileBytes + c * kKvChunkBytes, &tm_kv, &k_full[s], col_k + c * 16, row);
         }
         __syncwarp();
         mbar_wait(&v_empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&v_full[s], kTileBytes);
+          mbar_expect_tx(&v_full[s], kKvTileBytes);
           for (int c = 0; c < kChunks; ++c)
-            tma_load_2d(smem_v + s * kTileBytes + c * kChunkBytes, &tm_qkv, &v_full[s], col_v + c * 16, row);
+            tma_load_2d(smem_v + s * kKvTileBytes + c * kKvChunkBytes, &tm_kv, &v_full[s], col_v + c * 16, row);
         }
         __syncwarp();
       }
@@ -232,58 +244,48 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
       // ---------------------------------------------------------------- MMA issuers: warp 1 -> query tile 0, warp 2 -> tile 1
       // (warp-uniform loops, elected lane issues). Scores are double-buffered per query tile: S_t(i+2) is issued right
       // after P_t(i).V, two sub-steps ahead of the softmax that will read it, so the softmax warps do not wait for the
-      // tensor pipe. One issuing warp per tile: a single warp could not keep up with 18 MMAs per 64-key sub-step.
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);  // Q (K-major) x K (K-major), 64 keys
+      // tensor pipe. One issuing warp per tile: a single warp could not keep up with 20 MMAs per 80-key sub-step.
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);  // Q (K-major) x K (K-major), 80 keys
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd, 0, 1);   // P (TMEM) x V (MN-major)
       constexpr uint32_t hi32 = smem_desc_hi(256, 6);                 // SWIZZLE_32B, 8-row groups 256 B apart
       const int t = warp - 1;
       const uint32_t tmem_u = uniform_u32(tmem_base);
       const int n_sub_u = (int)uniform_u32(n_sub);
-      const uint32_t q_tm = tmem_u + Shape::q_col(t);  // Q_t as the A operand in TMEM (bf16 pairs, 8 columns per 16 dims)
+      const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16) + t * (kTileBytes >> 4);
       const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
-      const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kChunkBytes);  // LBO = distance between 16-column groups
+      const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kKvChunkBytes);  // LBO = distance between 16-column groups
       const uint32_t d_o = tmem_u + Shape::o_col(t);
       auto issue_s = [&](int i) {
-        const int s = (i >> 1) % kKvStages;
-        const uint32_t ka = k_lo + s * (kTileBytes >> 4) + (i & 1) * ((kSub * 32) >> 4);
-        const uint32_t d = tmem_u + t * 128 + (i & 1) * kSub;
+        const int s = i % kKvStages;
+        mbar_wait(&k_full[s], (i / kKvStages) & 1);
+        tc_fence_after();
+        const uint32_t ka = k_lo + s * (kKvTileBytes >> 4);
+        const uint32_t d = tmem_u + Shape::s_col(t, i & 1);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
-          umma_ts_lo(d, q_tm + c * 8, ka + c * (kChunkBytes >> 4), hi32, idesc_s, c != 0);
+          umma_ss_lo(d, q_lo + c * (kChunkBytes >> 4), ka + c * (kKvChunkBytes >> 4), hi32, idesc_s, c != 0);
         tc_commit_elect(&s_full[t * 2 + (i & 1)]);
+        tc_commit_elect(&k_empty[s]);
       };
       auto issue_pv = [&](int i) {
-        const int s = (i >> 1) % kKvStages;
-        const uint32_t va = v_lo + s * (kTileBytes >> 4) + (i & 1) * ((kSub * 32) >> 4);
-        const uint32_t pa = tmem_u + t * 128 + (i & 1) * kSub;
+        const int s = i % kKvStages;
+        mbar_wait(&v_full[s], (i / kKvStages) & 1);
+        mbar_wait(&p_full[t * 2 + (i & 1)], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t va = v_lo + s * (kKvTileBytes >> 4);
+        const uint32_t pa = tmem_u + Shape::s_col(t, i & 1);
 #pragma unroll
         for (int ks = 0; ks < kSub / 16; ++ks)  // 16 keys per step: rows ks*16.. of every chunk, 512 B further
           umma_ts_lo(d_o, pa + ks * 8, va + ks * (512 >> 4), hi32, idesc_o, (i > 0 || ks != 0));
         tc_commit_elect(&o_done[t * 2 + (i & 1)]);
+        tc_commit_elect(&v_empty[s]);
       };
-      mbar_wait(t == 0 ? q_full : q_full1, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
+      mbar_wait(q_full, 0);
       issue_s(0);
       if (n_sub_u > 1) issue_s(1);
-      tc_commit_elect(&k_empty[0]);
       for (int i = 0; i < n_sub_u; ++i) {
-        const int kt = i >> 1;
-        if ((i & 1) == 0) mbar_wait(&v_full[kt % kKvStages], (kt / kKvStages) & 1);
-        mbar_wait(&p_full[t * 2 + (i & 1)], (i >> 1) & 1);
-        tc_fence_after();
         issue_pv(i);
-        const int i2 = i + 2;
-        if (i2 < n_sub_u) {
-          const int kt2 = i2 >> 1;
-          if ((i2 & 1) == 0) {
-            mbar_wait(&k_full[kt2 % kKvStages], (kt2 / kKvStages) & 1);
-            tc_fence_after();
-          }
-          issue_s(i2);
-          if ((i2 & 1) == 1 || i2 == n_sub_u - 1) tc_commit_elect(&k_empty[kt2 % kKvStages]);
-        }
-        if ((i & 1) == 1 || i == n_sub_u - 1) tc_commit_elect(&v_empty[kt % kKvStages]);
+        if (i + 2 < n_sub_u) issue_s(i + 2);
       }
     }
   } else {
@@ -300,27 +302,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
     // phase - and the unit idles half the time. A token passed through two 64-thread named barriers makes them alternate.
     const int pp_mine = 1 + t * 4 + qtr, pp_other = 1 + (1 - t) * 4 + qtr;
     if (kPP && t == 1) named_bar_arrive(pp_other, 64);  // tile 0 goes first
-    {
-      // this thread's query row -> TMEM, as the A operand of S = Q K^T: Q is then read from shared memory by no MMA
-      // (a 128 x 64 x 16 MMA with both operands in shared memory is bound by its 6 KB of operand reads, not by the math)
-      uint32_t qw[kHd / 2];
-      const int qr = t * kTileRows + r;
-      if (qr < w.q_rows) {
-        const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(w.q_begin + qr) * (num_heads * 3 * kHd) + col_q);
-#pragma unroll
-        for (int c = 0; c < kHd / 8; ++c) {
-          const uint4 v = __ldg(src + c);
-          qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < kHd / 2; ++c) qw[c] = 0u;
-      }
-      tmem_st_cols<kHd / 2>(tmem_base + Shape::q_col(t) + lane_off, qw);
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(t == 0 ? q_full : q_full1);
-    }
     float m_ref = -INFINITY, l = 0.f;
     int w_lo = 0, w_hi = 0;  // this row's window, as key indices relative to kv_begin
     if (kWin) {
@@ -334,12 +315,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
     for (int i = 0; i < n_sub; ++i) {
       const int b = i & 1;                    // S/P buffer and barrier slot of this sub-step
       const uint32_t ph = (i >> 1) & 1;      // phase of s_full / p_full / o_done[b] for this sub-step
-      const uint32_t t_s = tmem_base + t * 128 + b * kSub + lane_off;
+      const uint32_t t_s = tmem_base + Shape::s_col(t, b) + lane_off;
       mbar_wait(&s_full[t * 2 + b], ph);
       tc_fence_after();
       uint32_t sr[kSub];
       tmem_ld_x32(t_s, sr);
       tmem_ld_x32(t_s + 32, sr + 32);
+      if constexpr (kSub == 80) tmem_ld_x16(t_s + 64, sr + 64);
       tc_wait_ld();
       const int c0 = i * kSub;  // key index (relative to kv_begin) of the first column
       if (kWin) {
@@ -412,6 +394,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16
       l = l * alpha + sum;
       tmem_st_x16(t_s, pk);
       tmem_st_x16(t_s + 16, pk + 16);
+      if constexpr (kSub == 80) tmem_st_x8(t_s + 32, pk + 32);
       // P.V completions are signalled on one barrier per S/P buffer, o_done[t][b]; every completion is observed, in
       // order - P_{i-2} V here, normally long done - so a parity wait stays unambiguous.
       if (i > 1) mbar_wait(&o_done[t * 2 + b], ph ^ 1);
@@ -465,11 +448,14 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
                      int64_t total_rows, cudaStream_t stream, const int2* d_win) {
   if (n_work <= 0) return KOCR_OK;
   if (num_heads <= 0 || num_heads > 65535) return fail(KOCR_ERR_UNSUPPORTED, "attention: bad head count");
-  CUtensorMap tm;
+  const int sub = d_win ? AttnShape<true>::kSub : AttnShape<false>::kSub;
+  CUtensorMap tm_q, tm_kv;
   uint64_t dims[2] = {(uint64_t)num_heads * 3 * kHd, (uint64_t)total_rows};
   uint64_t str[1] = {(uint64_t)num_heads * 3 * kHd * 2};
-  uint32_t box[2] = {16, kTileRows};
-  int rc = make_tensor_map(&tm, qkv, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  uint32_t box_q[2] = {16, kTileRows}, box_kv[2] = {16, (uint32_t)sub};
+  int rc = make_tensor_map(&tm_q, qkv, 2, dims, str, box_q, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (rc) return rc;
+  rc = make_tensor_map(&tm_kv, qkv, 2, dims, str, box_kv, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (rc) return rc;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -479,9 +465,9 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   }
   dim3 grid((unsigned)n_work, (unsigned)num_heads);
   if (d_win)
-    attention_kernel<true><<<grid, AttnShape<true>::kThreads, AttnShape<true>::kSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
+    attention_kernel<true><<<grid, AttnShape<true>::kThreads, AttnShape<true>::kSmem, stream>>>(tm_q, tm_kv, static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
   else
-    attention_kernel<false><<<grid, AttnShape<false>::kThreads, AttnShape<false>::kSmem, stream>>>(tm, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
+    attention_kernel<false><<<grid, AttnShape<false>::kThreads, AttnShape<false>::kSmem, stream>>>(tm_q, tm_kv, static_cast<__nv_bfloat16*>(out), d_work, num_heads, nullptr);
   KOCR_LAUNCH_CHECK("attention_kernel");
   return KOCR_OK;
 }

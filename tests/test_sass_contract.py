@@ -66,7 +66,7 @@ def test_attention_exponent_phase_is_between_the_hand_over_barriers(sass):
         inside = [i for i in mufu if sync[0] < i < arv[1]]
         after = [i for i in mufu if i > arv[1]]
         before = [i for i in mufu if i < sync[0]]
-        # 48 MUFU exponentials per 64-key sub-step (16 more go through the FMA-pipe polynomial) + 1 for the rescale factor
-        assert len(mufu) == 49, len(mufu)
+        # 60 MUFU exponentials per 80-key sub-step (20 more go through the FMA-pipe polynomial) + 1 for the rescale factor
+        assert len(mufu) == 61, len(mufu)
         assert len(before) <= 1, "exponentials were hoisted above the token wait"
-        assert len(inside) >= 36 and len(after) <= 12, (len(inside), len(after))
+        assert len(inside) >= 45 and len(after) <= 15, (len(inside), len(after))
