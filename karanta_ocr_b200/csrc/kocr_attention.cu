@@ -150,7 +150,7 @@ __device__ __forceinline__ uint64_t ex2_poly_f32x2(uint64_t x2) {
 }
 
 // kWin: block-diagonal attention inside a query block (Qwen2.5-VL windows, HF modeling_qwen2_5_vl.py:498-502): row r may
-// attend only the keys [win[r].x, win[r].y) of its own window; a 256-row block packs four or more windows.
+// attend only the keys [win[r].x, win[r].y) of its own window; a 128-row block packs two or more windows.
 template <bool kWin>
 __global__ void __launch_bounds__(AttnShape<kWin>::kThreads, kWin ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, __nv_bfloat16* __restrict__ out,
