@@ -72,3 +72,24 @@ def test_index_tables_match_oracle(grid):
     owi, ocuw = vo.window_index(g, 112, 2, 14)
     assert np.array_equal(wi, owi.astype(np.int32)) and np.array_equal(cuw[:ncw.value], ocuw.astype(np.int32))
     assert sorted(wi.tolist()) == list(range(total // 4))  # a permutation of the 4-patch groups
+
+
+@settings(max_examples=200, deadline=None)
+@given(costs=st.lists(st.floats(min_value=0.5, max_value=1e6, allow_nan=False), min_size=0, max_size=200), world=st.integers(1, 8))
+def test_shard_pages_is_a_balanced_partition(costs, world):
+    from karanta_ocr_b200 import gather_pages, shard_pages
+    shards = shard_pages(costs, world)
+    assert len(shards) == world
+    flat = sorted(i for s in shards for i in s)
+    assert flat == list(range(len(costs)))                      # every page exactly once
+    assert all(s == sorted(s) for s in shards)                  # each rank keeps input order
+    if costs:
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) <= sum(costs) / world + max(costs) + 1e-6 * sum(costs)  # greedy LPT bound
+    # the host-side gather puts per-rank results back in page order (single process: identity routing)
+    merged = [None] * len(costs)
+    for s in shards:
+        part = gather_pages([f"page{i}" for i in s], s, len(costs))
+        for i in s:
+            merged[i] = part[i]
+    assert merged == [f"page{i}" for i in range(len(costs))]
