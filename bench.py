@@ -117,16 +117,14 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(blocks_sampled=2, dtype=torch.float32, use_hf=True):
-    """One bounded sample of the workload on the host cores: ONE letter page through the reference's CPU path
-    (image processor in full; tower = patch-embed + `blocks_sampled` of the 32 identical blocks + merger), with the page
-    time extrapolated as t_proc + t_rest + 32 * t_block.  Returns (seconds_per_page, kind, description)."""
-    from oracle import preprocess_oracle as po
-    from oracle import vision_oracle as vo
+def cpu_reference_page(dtype=torch.float32, use_hf=True):
+    """The reference's CPU path for ONE letter page of the C2 workload, nothing sampled or extrapolated: the transformers
+    image processor, then the full 32-block Qwen2-VL-7B vision tower (sdpa attention) on all host threads. Falls back to
+    the oracle port (same arithmetic, oracle/) only when transformers cannot be imported.
+    Returns (run_once() -> seconds for the page, kind, description)."""
     torch.set_num_threads(os.cpu_count())
     page = make_pages(1)[0]
-    kind = "port"
-    proc = None
+    kind, proc, model = "port", None, None
     if use_hf:
         try:
             os.environ.setdefault("HF_HUB_OFFLINE", "1")
@@ -134,48 +132,35 @@ def cpu_reference_sample(blocks_sampled=2, dtype=torch.float32, use_hf=True):
             from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor
             from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VisionTransformerPretrainedModel
             proc = Qwen2VLImageProcessor(min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS)
-
-            def tower(depth):
-                c = Qwen2VLVisionConfig(depth=depth, embed_dim=1280, hidden_size=3584, mlp_ratio=4, num_heads=16)
-                c._attn_implementation = "sdpa"
-                torch.manual_seed(0)
-                return Qwen2VisionTransformerPretrainedModel(c).eval().to(dtype)
-            m_d, m_0 = tower(blocks_sampled), tower(0)
+            c = Qwen2VLVisionConfig(depth=32, embed_dim=1280, hidden_size=3584, mlp_ratio=4, num_heads=16)
+            c._attn_implementation = "sdpa"
+            torch.manual_seed(0)
+            model = Qwen2VisionTransformerPretrainedModel(c).eval().to(dtype)
             kind = "reference"
         except Exception:
-            proc = None
+            proc = model = None
     state = {}
 
     def run_once():
         t0 = time.perf_counter()
-        if proc is not None:
-            f = proc(images=[torch.from_numpy(page)], return_tensors="pt")
-            pv, grid = f["pixel_values"], f["image_grid_thw"]
-        else:
-            pv_np, grid = po.preprocess([page], MIN_PIXELS, MAX_PIXELS, po.RESIZE_ATEN)
-            pv = torch.from_numpy(pv_np)
-        t1 = time.perf_counter()
         with torch.no_grad():
-            if proc is not None:
-                m_0(pv.to(dtype), grid_thw=grid)
-                t2 = time.perf_counter()
-                m_d(pv.to(dtype), grid_thw=grid)
-                t3 = time.perf_counter()
+            if model is not None:
+                f = proc(images=[torch.from_numpy(page)], return_tensors="pt")
+                out = model(f["pixel_values"].to(dtype), grid_thw=f["image_grid_thw"])
+                out = getattr(out, "pooler_output", out)
             else:
+                from oracle import preprocess_oracle as po
+                from oracle import vision_oracle as vo
                 if "sd" not in state:
-                    state["cfg0"], state["cfgd"] = vo.qwen2_vl_7b(0), vo.qwen2_vl_7b(blocks_sampled)
-                    state["sd"] = vo.init_weights(state["cfgd"], seed=0)
-                vo.tower_forward(state["cfg0"], state["sd"], pv, grid, dtype)
-                t2 = time.perf_counter()
-                vo.tower_forward(state["cfgd"], state["sd"], pv, grid, dtype)
-                t3 = time.perf_counter()
-        t_proc, t_rest, t_d = t1 - t0, t2 - t1, t3 - t2
-        t_block = max(t_d - t_rest, 1e-9) / blocks_sampled
-        return t_proc + t_rest + 32 * t_block
-    desc = (f"1 letter page per step on {os.cpu_count()} host threads, {str(dtype).replace('torch.', '')}: image processor in full + tower "
-            f"(patch-embed, {blocks_sampled} of 32 identical blocks, merger) via "
-            f"{'transformers ' + __import__('transformers').__version__ if kind == 'reference' else 'the oracle port'}; "
-            f"page time = t_proc + t_rest + 32*t_block")
+                    state["cfg"] = vo.qwen2_vl_7b(32)
+                    state["sd"] = vo.init_weights(state["cfg"], seed=0)
+                pv_np, grid = po.preprocess([page], MIN_PIXELS, MAX_PIXELS, po.RESIZE_ATEN)
+                out = vo.tower_forward(state["cfg"], state["sd"], torch.from_numpy(pv_np), grid, dtype)
+        assert tuple(out.shape) == (1656, 3584), out.shape
+        return time.perf_counter() - t0
+    desc = (f"1 letter page per step (of the workload's 64) on {os.cpu_count()} host threads, {str(dtype).replace('torch.', '')}: image processor "
+            f"+ the full 32-block tower, measured (nothing extrapolated), via "
+            f"{'transformers ' + __import__('transformers').__version__ if kind == 'reference' else 'the oracle port'}")
     return run_once, kind, desc
 
 
@@ -183,18 +168,43 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run_once, kind, desc = cpu_reference_sample()
-    for _ in range(max(args.warmup, 1)):
+    run_once, kind, desc = cpu_reference_page()
+    t_first = run_once()
+    # every timed step is a real full-depth page; warm-up is cut to the first page only when W + K pages would not fit the budget
+    budget = float(os.environ.get("KOCR_REF_BUDGET_S", "1200"))
+    warm = max(args.warmup, 1) if t_first * (args.warmup + args.steps) <= budget else 1
+    for _ in range(warm - 1):
         run_once()
+    t0 = time.perf_counter()
     ts = [run_once() for _ in range(args.steps)]
-    spp = float(np.mean(ts))
+    wall = time.perf_counter() - t0
+    spp = wall / args.steps
     value = 1.0 / spp
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "pages_per_step": 1},
+            "warmup": args.warmup, "warmup_done": warm, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pages_per_step": 1,
+                       "note": "a reference step is ONE page of the 64-page batch (bounded sample); pages/s = steps / wall time of the timed steps"},
+            "ms_per_page_min_max": [min(ts) * 1e3, max(ts) * 1e3],
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def library_baselines(pages=16, steps=3, timeout_s=300):
+    """The two library towers a user of the reference could run on this same GPU today (last row):
+    transformers + flash-attn 2 / sdpa, and vLLM's Qwen2VisionTransformer with its FA4 back-end; 16 C2 pages, bf16, tower
+    only. Each runs in its own process (vLLM initialises a process group) after this process has finished timing."""
+    out = []
+    for tool in ("hf_gpu_baseline.py", "vllm_gpu_baseline.py"):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), str(pages), str(steps)], capture_output=True,
+                               text=True, timeout=timeout_s)
+            got = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out += got if got else [{"impl": tool, "unavailable": (r.stderr or "no output")[-300:]}]
+        except Exception as e:
+            out.append({"impl": tool, "unavailable": f"{type(e).__name__}: {str(e)[:200]}"})
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -352,10 +362,15 @@ def run_gpu(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
-            run_once, kind, desc = cpu_reference_sample()
-            run_once()
-            spp = float(np.mean([run_once() for _ in range(2)]))
+            run_once, kind, desc = cpu_reference_page()
+            run_once()                       # warm-up page (thread pools, oneDNN primitive caches)
+            spp = run_once()                 # one full-depth page: the bounded CPU sample (~10-30 s)
             line["cpu_baseline"] = {"value": 1.0 / spp, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": desc}
+        if world == 1 and args.library_baselines and args.workload == "c2":
+            del d_pages, h_pages
+            torch.cuda.empty_cache()
+            line["extra"] = {"library_baselines_same_gpu": library_baselines(),
+                             "note": "tower only, 16 C2 pages per call, bf16, random weights; 'this repo' line in the same list for the like-for-like"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -452,6 +467,8 @@ def main():
     ap.add_argument("--impl", default="kocr", choices=["kocr", "reference"])
     ap.add_argument("--pages", type=int, default=PAGES_PER_STEP, help="pages per step per GPU (C2 = 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baselines", dest="library_baselines", action="store_false",
+                    help="skip timing the transformers (flash-attn 2 / sdpa) and vLLM (FA4) towers on this GPU after the run (line['extra'])")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = the metric's configuration (default); c3 / c4 = the other BASELINE.json configs, for the record; "
                          "c5 = one bulk job of --job-pages pages sharded over the ranks (strong scaling)")

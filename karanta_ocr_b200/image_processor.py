@@ -104,12 +104,7 @@ class KarantaImageProcessor:
             size["longest_edge"] = max_pixels
         if "shortest_edge" not in size or "longest_edge" not in size:
             raise ValueError("size must contain 'shortest_edge' and 'longest_edge' keys.")
-        for k in ("patch_size", "temporal_patch_size", "merge_size"):
-            if k in kwargs and kwargs[k] != getattr(type(self), k):
-                raise ValueError(f"{k}={kwargs[k]} is not supported: the kernel is built for 14 / 2 / 2")
-        for k, ref in (("image_mean", OPENAI_CLIP_MEAN), ("image_std", OPENAI_CLIP_STD)):
-            if k in kwargs and kwargs[k] is not None and [float(v) for v in kwargs[k]] != ref:
-                raise ValueError(f"{k} other than the OPENAI_CLIP constants is not supported")
+        self._check_fixed_kwargs(kwargs)
         if resize_backend not in ("torchvision", "pil"):
             raise ValueError("resize_backend must be 'torchvision' or 'pil'")
         self.size = size
@@ -118,6 +113,20 @@ class KarantaImageProcessor:
         self.device = torch.device(device) if device is not None else None
         self._pinned = None
         self._pinned_ev = None
+
+    @classmethod
+    def _check_fixed_kwargs(cls, kwargs):
+        """Options the kernel is built around: a different value is an error, never silently ignored."""
+        for k in ("patch_size", "temporal_patch_size", "merge_size"):
+            if kwargs.get(k) is not None and kwargs[k] != getattr(cls, k):
+                raise ValueError(f"{k}={kwargs[k]} is not supported: the kernel is built for 14 / 2 / 2")
+        for k, ref in (("image_mean", OPENAI_CLIP_MEAN), ("image_std", OPENAI_CLIP_STD)):
+            if kwargs.get(k) is not None and [float(v) for v in kwargs[k]] != ref:
+                raise ValueError(f"{k} other than the OPENAI_CLIP constants is not supported")
+        if kwargs.get("resample") is not None and int(kwargs["resample"]) != 3:
+            raise ValueError("resample other than BICUBIC (3) is not supported")
+        if kwargs.get("rescale_factor") is not None and float(kwargs["rescale_factor"]) != 1 / 255:
+            raise ValueError("rescale_factor other than 1/255 is not supported")
 
     @property
     def min_pixels(self):
@@ -228,6 +237,13 @@ class KarantaImageProcessor:
                 raise ValueError(f"{k}=False is not supported by the fused kernel")
         if kwargs.get("videos") is not None:
             raise ValueError("video input is not supported on this path (karanta-ocr sends still pages)")
+        self._check_fixed_kwargs(kwargs)
+        size = kwargs.get("size")
+        if size is not None:  # call-time size= has the constructor's meaning (HF image_processing_qwen2_vl.py:148-166)
+            if "shortest_edge" not in size or "longest_edge" not in size:
+                raise ValueError("size must contain 'shortest_edge' and 'longest_edge' keys.")
+            min_pixels = size["shortest_edge"] if min_pixels is None else min_pixels
+            max_pixels = size["longest_edge"] if max_pixels is None else max_pixels
         pv, grid = self.preprocess_device(images, torch.float32, min_pixels, max_pixels)
         target = torch.device(device) if device is not None else (self.device or torch.device("cpu"))
         if target.type == "cpu":

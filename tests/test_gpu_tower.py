@@ -1,6 +1,9 @@
 """GPU parity of the whole path through the Python surface that mirrors transformers: KarantaVisionTower against the
-fp32 CPU oracle and the golden embeddings minted from transformers. Tolerance (north_star): cosine >= 0.999 per image
-and max|d| / max|y_fp32| <= 5e-2 for the bf16 tower."""
+fp32 CPU oracle and the golden embeddings minted from transformers. Tolerance (north_star):
+cosine >= 0.999 per image, and max|d| / max|y_fp32| <= tau with tau CALIBRATED as 1.5 x the error the reference
+implementation itself shows when it runs in bf16 on the same inputs and weights: for the golden cases that error was
+recorded from transformers by tests/golden/make_golden.py (`*.hf_bf16_max_rel`: 0.0066-0.0076 at depth 2-3, 0.016-0.019
+at depth 32), for oracle-compared cases the oracle is run a second time in bf16."""
 import os
 
 import numpy as np
@@ -14,7 +17,14 @@ from tests.synth import synth_page
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 CKPT_MAX = 12845056
-COS_MIN, REL_MAX = 0.999, 5e-2
+COS_MIN = 0.999
+TAU_FACTOR = 1.5
+
+
+def _tau_from_oracle(cfg, sd, pv, grid, ref32):
+    """1.5 x max-rel error of the reference algorithm in bf16 (same inputs, same weights) against its own fp32 result."""
+    refb = vo.tower_forward(cfg, sd, torch.as_tensor(pv), grid, dtype=torch.bfloat16).float()
+    return TAU_FACTOR * ((refb - ref32).abs().max() / ref32.abs().max()).item()
 
 
 def _tower(cfg, seed=100):
@@ -26,7 +36,7 @@ def _tower(cfg, seed=100):
     return t
 
 
-def _check(out, ref, grid, what):
+def _check(out, ref, grid, what, rel_max):
     out = out.float().cpu()
     ref = torch.as_tensor(ref).float()
     assert out.shape == ref.shape, (out.shape, ref.shape)
@@ -35,7 +45,8 @@ def _check(out, ref, grid, what):
     sizes = (np.asarray(grid).reshape(-1, 3).prod(-1) // 4).tolist()
     coss = [torch.nn.functional.cosine_similarity(a.reshape(1, -1), b.reshape(1, -1)).item()
             for a, b in zip(torch.split(out, sizes), torch.split(ref, sizes))]
-    assert min(coss) >= COS_MIN and rel <= REL_MAX, (what, min(coss), rel)
+    print(f"parity {what}: min cosine {min(coss):.6f} max-rel {rel:.5f} (tau {rel_max:.5f})")
+    assert min(coss) >= COS_MIN and rel <= rel_max, (what, min(coss), rel, rel_max)
     return min(coss), rel
 
 
@@ -58,7 +69,7 @@ def test_tower_vs_transformers_golden(name):
     tower = _tower(cfg)
     out = tower(feats["pixel_values"], grid_thw=feats["image_grid_thw"])
     assert out.dtype == torch.bfloat16 and out.device.type == "cuda"
-    _check(out, z[f"{name}.emb"], z[f"{name}.grid"], name)
+    _check(out, z[f"{name}.emb"], z[f"{name}.grid"], name, TAU_FACTOR * float(z[f"{name}.hf_bf16_max_rel"]))
 
 
 def test_c1_qwen2vl_2b_sample_page():
@@ -76,7 +87,69 @@ def test_c1_qwen2vl_2b_sample_page():
     ref = torch.from_numpy(z["c1_q2_2b.emb"])
     rel = ((sub - ref).abs().max() / float(z["c1_q2_2b.emb_absmax"])).item()
     cos = torch.nn.functional.cosine_similarity(sub.reshape(1, -1), ref.reshape(1, -1)).item()
-    assert cos >= COS_MIN and rel <= REL_MAX, (cos, rel)
+    tau = TAU_FACTOR * float(z["c1_q2_2b.hf_bf16_max_rel"])
+    print(f"parity C1: cosine {cos:.6f} max-rel {rel:.5f} (tau {tau:.5f})")
+    assert cos >= COS_MIN and rel <= tau, (cos, rel, tau)
+
+
+DEPTH32 = {   # name -> (tower config, [(h, w, seed)] of make_golden.g7_depth32)
+    "c2_q2_7b": (vo.qwen2_vl_7b(), [(1288, 995, 1234)]),
+    "c3_q25_7b": (vo.qwen2_5_vl_7b(), [(1288, 995, 1234)]),
+    "c4_q2_7b": (vo.qwen2_vl_7b(), [(1288, 420, 1237), (640, 880, 1241), (256, 256, 1242), (1288, 910, 1235)]),
+    "c4_q25_7b": (vo.qwen2_5_vl_7b(), [(1288, 420, 1237), (640, 880, 1241), (256, 256, 1242), (1288, 910, 1235)]),
+}
+
+
+@pytest.mark.parametrize("name", list(DEPTH32))
+def test_depth32_baseline_configs_vs_transformers_golden(name):
+    """BASELINE configs at their own size: C2 (Qwen2-VL-7B, depth 32, one 6624-patch letter page), C3 (Qwen2.5-VL-7B,
+    depth 32, full attention in blocks 7/15/23/31) and the C4 mixed-aspect batch through both towers, against fp32
+    transformers (tests/golden/g7_depth32.npz, every 16th row). tau = 1.5 x transformers' own bf16 error on the case."""
+    from karanta_ocr_b200 import PageEncoder
+    z = np.load(os.path.join(G, "g7_depth32.npz"))
+    cfg, specs = DEPTH32[name]
+    assert cfg.depth == 32 and (cfg.arch == "qwen2_vl" or tuple(cfg.fullatt_block_indexes) == (7, 15, 23, 31))
+    pages = [synth_page(h, w, seed) for h, w, seed in specs]
+    emb, grid = PageEncoder(_tower(cfg)).encode(pages)
+    assert np.array_equal(grid.numpy(), z[f"{name}.grid"])
+    stride = int(z[f"{name}.emb_rows_stride"])
+    out = emb.float().cpu()
+    assert torch.isfinite(out).all()
+    ref = torch.from_numpy(z[f"{name}.emb"])
+    sub = out[::stride]
+    assert sub.shape == ref.shape
+    tau = TAU_FACTOR * float(z[f"{name}.hf_bf16_max_rel"])
+    rel = ((sub - ref).abs().max() / float(z[f"{name}.emb_absmax"])).item()
+    # per-page cosine over the page's sampled rows
+    sizes = (z[f"{name}.grid"].prod(-1) // 4).tolist()
+    page_of_row = np.repeat(np.arange(len(sizes)), sizes)[::stride]
+    coss = []
+    for pg in range(len(sizes)):
+        m = torch.from_numpy(page_of_row == pg)
+        coss.append(torch.nn.functional.cosine_similarity(sub[m].double().reshape(1, -1), ref[m].double().reshape(1, -1)).item())
+    print(f"parity {name}: per-page cosine {['%.6f' % c for c in coss]} max-rel {rel:.5f} (tau {tau:.5f}; transformers bf16 "
+          f"{float(z[f'{name}.hf_bf16_max_rel']):.5f}, its min cosine {float(z[f'{name}.hf_bf16_min_cos']):.6f})")
+    assert min(coss) >= COS_MIN and rel <= tau, (name, coss, rel, tau)
+
+
+def test_depth32_c2_batch64_equals_single_pages():
+    """The benchmarked batch (64 letter pages, Qwen2-VL-7B, depth 32) gives every page the embeddings it gets alone,
+    bit for bit: nothing in the 32 blocks couples pages (block-diagonal attention, per-row epilogues and statistics)."""
+    from karanta_ocr_b200 import PageEncoder
+    enc = PageEncoder(_tower(vo.qwen2_vl_7b()))
+    pages = [synth_page(1288, 995, 1234 + i) for i in range(64)]
+    emb, grid = enc.encode(pages)
+    assert grid.tolist() == [[1, 92, 72]] * 64 and emb.shape == (64 * 1656, 3584)
+    parts = torch.split(emb, 1656)
+    for i in (0, 1, 31, 63):
+        one, _ = enc.encode([pages[i]])
+        assert torch.equal(one, parts[i]), i
+    # and page 0 is the page of the depth-32 golden: the batch result is pinned to transformers, not only to itself
+    z = np.load(os.path.join(G, "g7_depth32.npz"))
+    ref = torch.from_numpy(z["c2_q2_7b.emb"])
+    sub = parts[0].float().cpu()[::int(z["c2_q2_7b.emb_rows_stride"])]
+    rel = ((sub - ref).abs().max() / float(z["c2_q2_7b.emb_absmax"])).item()
+    assert rel <= TAU_FACTOR * float(z["c2_q2_7b.hf_bf16_max_rel"]), rel
 
 
 @pytest.mark.parametrize("arch", ["qwen2_vl", "qwen2_5_vl"])
@@ -90,8 +163,9 @@ def test_mixed_varlen_batch_vs_oracle(arch):
     emb, grid = PageEncoder(tower).encode(pages)
     pv, g = po.preprocess(pages, 3136, CKPT_MAX, po.RESIZE_ATEN)
     assert np.array_equal(grid.numpy(), g)
-    ref = vo.tower_forward(cfg, vo.init_weights(cfg, seed=100), torch.from_numpy(pv), g)
-    _check(emb, ref, g, arch)
+    sd = vo.init_weights(cfg, seed=100)
+    ref = vo.tower_forward(cfg, sd, torch.from_numpy(pv), g)
+    _check(emb, ref, g, arch, _tau_from_oracle(cfg, sd, pv, g, ref))
 
 
 def test_padded_3d_pixel_values_are_flattened():
@@ -127,8 +201,9 @@ def test_full_letter_page_depth4_vs_oracle():
     assert grid.tolist() == [[1, 92, 72]] and emb.shape == (1656, 3584)
     pv, g = po.preprocess([page], 3136, CKPT_MAX, po.RESIZE_ATEN)
     torch.set_num_threads(os.cpu_count())
-    ref = vo.tower_forward(cfg, vo.init_weights(cfg, seed=100), torch.from_numpy(pv), g)
-    _check(emb, ref, g, "letter_d4")
+    sd = vo.init_weights(cfg, seed=100)
+    ref = vo.tower_forward(cfg, sd, torch.from_numpy(pv), g)
+    _check(emb, ref, g, "letter_d4", _tau_from_oracle(cfg, sd, pv, g, ref))
 
 
 def test_batch_equals_single_pages():
@@ -164,11 +239,14 @@ def test_drop_in_for_transformers_model():
     with torch.no_grad():
         ref32 = model.float().get_image_features(pv, grid).pooler_output       # fp32 on the GPU: the tolerance anchor
         model.to(torch.bfloat16)
+        model_hf_bf16_out = model.get_image_features(pv.to(torch.bfloat16), grid).pooler_output  # transformers' own bf16 error
         tower = KarantaVisionTower.replace_visual(model)
         assert model.visual is tower
         got = model.get_image_features(pv.to(torch.bfloat16), grid).pooler_output
     assert len(got) == 2 and [g.shape for g in got] == [r.shape for r in ref32]
-    _check(torch.cat(list(got)), torch.cat(list(ref32)).cpu(), grid.cpu().numpy(), "hf_drop_in")
+    r32, rb = torch.cat(list(ref32)), torch.cat(list(model_hf_bf16_out)).float()
+    tau = TAU_FACTOR * ((rb - r32).abs().max() / r32.abs().max()).item()
+    _check(torch.cat(list(got)), torch.cat(list(ref32)).cpu(), grid.cpu().numpy(), "hf_drop_in", tau)
 
 
 @pytest.mark.parametrize("arch", ["qwen2_vl", "qwen2_5_vl"])
@@ -195,4 +273,4 @@ def test_norm_folding_with_outlier_channels(arch):
     x0 = torch.nn.functional.linear(torch.from_numpy(pv), sd["patch_embed.proj.weight"].reshape(1280, -1))
     assert (x0.mean(-1).abs() / x0.std(-1)).median() > 0.02 and x0.abs().max() > 50 * x0.abs().median()  # the regime is the intended one
     ref = vo.tower_forward(cfg, sd, torch.from_numpy(pv), gg)
-    _check(emb, ref, gg, f"outliers_{arch}")
+    _check(emb, ref, gg, f"outliers_{arch}", _tau_from_oracle(cfg, sd, pv, gg, ref))

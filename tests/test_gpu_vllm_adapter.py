@@ -85,7 +85,7 @@ def test_adapter_matches_vllm_tower(vllm_env, arch):
     cos = torch.nn.functional.cosine_similarity(out.flatten(), ref.flatten(), dim=0).item()
     rel = ((out - ref).abs().max() / ref.abs().max()).item()
     print(f"vllm adapter {arch}: cosine {cos:.6f} rel-max {rel:.4f}")
-    assert cos >= 0.999 and rel <= 0.06  # two bf16 implementations against each other (each is within 5e-2 of fp32)
+    assert cos >= 0.999 and rel <= 0.03  # two bf16 towers against each other: each within tau = 1.5 x 0.0076 of fp32 at depth 3 (g5 golden), so <= 2 tau + margin
 
 
 def test_replace_vllm_visual_swaps_module(vllm_env):

@@ -9,7 +9,8 @@ __global__ void k(float* out, int iters, float seed) {
   float a[16];
   uint64_t p[8];
   uint32_t u[16];
-  for (int i = 0; i < 16; ++i) { a[i] = seed + i * 0.01f + threadIdx.x * 1e-4f; u[i] = threadIdx.x * 3 + i; }
+  unsigned short h[16];
+  for (int i = 0; i < 16; ++i) { a[i] = seed + i * 0.01f + threadIdx.x * 1e-4f; u[i] = threadIdx.x * 3 + i; h[i] = (unsigned short)(threadIdx.x + i); }
   for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
   const float c = seed * 0.5f;
   uint64_t c2;
@@ -33,11 +34,22 @@ __global__ void k(float* out, int iters, float seed) {
         if (OP == 8) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
         if (OP == 9) asm volatile("shf.l.wrap.b32 %0, %0, %1, 23;" : "+r"(u[i]) : "r"(u[(i + 1) & 15]));
         if (OP == 10) asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 15]));
+        if (OP == 11) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));
+        if (OP == 12) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+        if (OP == 13) {
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[(i + 1) & 15]));
+          a[i] = __uint_as_float(u[i]);
+        }
+        if (OP == 14) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 15]));
+        if (OP == 15) asm volatile("fma.rn.bf16x2 %0, %0, %1, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 15]));
+        if (OP == 16) asm volatile("ex2.approx.ftz.bf16 %0, %0;" : "+h"(h[i]));
+        if (OP == 17) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
+        if (OP == 18) asm volatile("sub.rn.bf16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 15]));
       }
     }
   }
   float s = 0;
-  for (int i = 0; i < 16; ++i) s += a[i] + (float)u[i];
+  for (int i = 0; i < 16; ++i) s += a[i] + (float)u[i] + (float)h[i];
   for (int i = 0; i < 8; ++i) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p[i])); s += x + y; }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
@@ -75,5 +87,13 @@ int main() {
   run<8>("ex2.approx.f32");
   run<9>("shf.l.wrap.b32");
   run<10>("max.bf16x2");
+  run<11>("ex2.approx.ftz.bf16x2");
+  run<12>("ex2.approx.f16x2");
+  run<13>("cvt.rn.f16x2.f32");
+  run<14>("add.rn.f16x2");
+  run<15>("fma.rn.bf16x2");
+  run<16>("ex2.approx.ftz.bf16");
+  run<17>("tanh.approx.f32");
+  run<18>("sub.rn.bf16x2");
   return 0;
 }
