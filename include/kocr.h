@@ -162,6 +162,13 @@ KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int 
                        int n_images, void* out, void* hidden_out, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
+/* The tables kocr_tower_forward derives from grid_thw alone (patch positions for rot_pos_emb, HF modeling_qwen2_vl.py:
+ * 725-752; cu_seqlens :772-780 as attention work lists; Qwen2.5-VL window index / per-row window bounds, HF
+ * modeling_qwen2_5_vl.py:411-451) are planned once per distinct grid_thw and kept in HBM by the tower (up to 16 plans, least
+ * recently used evicted): a forward over a grid seen before does no host planning and no table upload.  Counters for tests
+ * and monitoring: forwards served from a cached plan / forwards that had to plan. */
+KOCR_API int kocr_tower_plan_stats(const KocrTower* tower, int64_t* hits, int64_t* misses);
+
 /* ------------------------------------------------------------------ LLM hand-off */
 
 /* Host planning (no GPU): 3-D M-RoPE position ids of a text+image prompt.  Stands in for
@@ -174,6 +181,19 @@ KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int 
 KOCR_API int kocr_mrope_position_ids(const int64_t* input_ids, const int64_t* attention_mask, int batch, int seq_len,
                                      const int64_t* image_grid_thw, int n_images, int64_t image_token_id, int merge,
                                      int64_t* position_ids, int64_t* deltas);
+
+/* Same, with the transformers line selectable.  KOCR_MROPE_TRANSFORMERS_5 is kocr_mrope_position_ids (pinned by
+ * tests/golden/g6_llm_handoff.npz, minted from transformers 5.5.0).  KOCR_MROPE_TRANSFORMERS_4_5 follows the 4.5x
+ * get_rope_index the reference pins (4.53.3, /root/reference/uv.lock:2168-2169): padded positions hold 1, deltas are taken
+ * against the PADDED row length (what generate() adds to cache_position for left-padded batches), images are located by
+ * vision_start_token_id (< 0: by runs of image tokens) and consume exactly their grid's token count, so adjacent images need
+ * no separator.  4.5x is not installed in the build image: that mode is restated from its source and has no golden. */
+#define KOCR_MROPE_TRANSFORMERS_5 0
+#define KOCR_MROPE_TRANSFORMERS_4_5 1
+KOCR_API int kocr_mrope_position_ids_v2(const int64_t* input_ids, const int64_t* attention_mask, int batch, int seq_len,
+                                        const int64_t* image_grid_thw, int n_images, int64_t image_token_id,
+                                        int64_t vision_start_token_id, int merge, int semantics, int64_t* position_ids,
+                                        int64_t* deltas);
 
 /* inputs_embeds.masked_scatter(input_ids == image_token_id, image_embeds) on the device, in place.  Stands in for
  * get_placeholder_mask + masked_scatter (HF modeling_qwen2_vl.py:1138-1177 and the forward's

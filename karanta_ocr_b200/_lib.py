@@ -51,8 +51,11 @@ SIGNATURES = {
     "kocr_tower_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int]),
     "kocr_tower_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
+    "kocr_tower_plan_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kocr_mrope_position_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                           C.c_void_p]),
+    "kocr_mrope_position_ids_v2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p]),
     "kocr_scatter_image_embeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int64, C.c_void_p]),
     "kocr_last_launch_count": (C.c_int64, []),

@@ -457,12 +457,8 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   if (rc) return rc;
   rc = make_tensor_map(&tm_kv, qkv, 2, dims, str, box_kv, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (rc) return rc;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnShape<false>::kSmem));
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnShape<true>::kSmem));
-    attr_set = true;
-  }
+  if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&attention_kernel<false>), AttnShape<false>::kSmem))) return rc;
+  if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&attention_kernel<true>), AttnShape<true>::kSmem))) return rc;
   dim3 grid((unsigned)n_work, (unsigned)num_heads);
   if (d_win)
     attention_kernel<true><<<grid, AttnShape<true>::kThreads, AttnShape<true>::kSmem, stream>>>(tm_q, tm_kv, static_cast<__nv_bfloat16*>(out), d_work, num_heads, d_win);
@@ -523,8 +519,10 @@ extern "C" int kocr_op_attention(KocrCtx* ctx_, const void* qkv, void* out, cons
   int rc = build_attn_work(cu_seqlens_host, n_seqs, &work);
   if (rc) return rc;
   void* d_work;
-  rc = ctx->stage(work.data(), work.size() * sizeof(AttnWork), stream, &d_work);
+  int slot = -1;
+  rc = ctx->stage(work.data(), work.size() * sizeof(AttnWork), stream, &d_work, &slot);
   if (rc) return rc;
+  StageGuard guard(ctx, slot, stream);  // released after the kernel that reads the work list is enqueued
   return launch_attention(ctx, qkv, out, static_cast<const AttnWork*>(d_work), (int)work.size(), num_heads,
                           cu_seqlens_host[n_seqs], stream, nullptr);
 }

@@ -7,6 +7,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "../../include/kocr.h"
@@ -61,11 +63,20 @@ struct Ctx {
   void* d_slot[kSlots] = {};
   cudaEvent_t slot_ev[kSlots] = {};
   int next_slot = 0;
+  std::mutex slot_mu;            // next_slot / slot_open (entry points may be called from several host threads)
+  bool slot_open[kSlots] = {};   // staged, consumers possibly not enqueued yet: not reusable until released
   // stage `bytes` from host memory into a device slot on `stream`; returns the device pointer
-  int stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out);
+  int stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out, int* slot_out = nullptr);
   // begin/commit variant: fill the pinned slot in place
   int stage_begin(size_t bytes, void** h_out, int* slot);
   int stage_commit(int slot, size_t bytes, cudaStream_t stream, void** d_out);
+  // the last kernel that reads the slot has been enqueued on `stream`: the slot may be reused once the stream gets here.
+  // (Reuse waits for this event, not for the H2D copy alone: slots are shared by every stream that uses the context.)
+  void stage_release(int slot, cudaStream_t stream);
+  // MaxDynamicSharedMemorySize opt-ins already made on THIS device (the attribute is per device, not per thread)
+  std::mutex attr_mu;
+  std::set<const void*> smem_attr_done;
+  int opt_in_smem(const void* func, int bytes);
   // optional per-kernel-class timing with CUDA events on the launching stream (kocr_profile_begin / _end)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int cls; };
@@ -76,6 +87,17 @@ struct Ctx {
 
 enum ProfClass { kProfPreprocess = 0, kProfPatchEmbed, kProfNorm, kProfQkvRope, kProfAttention, kProfProj, kProfFc1, kProfFc2,
                  kProfMerger, kProfOther, kProfClasses };
+
+// Releases a staging slot at scope exit (after the consumers were enqueued, or on an early error return).
+struct StageGuard {
+  Ctx* ctx;
+  int slot;
+  cudaStream_t st;
+  StageGuard(Ctx* c, int s, cudaStream_t stream) : ctx(c), slot(s), st(stream) {}
+  ~StageGuard() { if (ctx && slot >= 0) ctx->stage_release(slot, st); }
+  StageGuard(const StageGuard&) = delete;
+  StageGuard& operator=(const StageGuard&) = delete;
+};
 
 // Records an event pair around the launches issued in its scope when profiling is on; free otherwise.
 struct ProfScope {

@@ -419,11 +419,7 @@ static int launch_one(Ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, co
                       int K, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   auto kern = gemm_kernel<BN, EPI>;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  if (int rc = ctx->opt_in_smem(reinterpret_cast<const void*>(kern), S::kTotal)) return rc;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = std::min(tiles, ctx->num_sms);
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep, M, N, K);

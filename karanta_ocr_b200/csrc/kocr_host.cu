@@ -263,26 +263,63 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 // ---- context
 int Ctx::stage_begin(size_t bytes, void** h_out, int* slot) {
   if (bytes > kSlotBytes) return fail(KOCR_ERR_UNSUPPORTED, "planning table larger than the staging slot");
-  int s = next_slot;
-  next_slot = (next_slot + 1) % kSlots;
-  KOCR_CUDA_CHECK(cudaEventSynchronize(slot_ev[s]));  // slot reuse: normally long complete
+  int s = -1;
+  {
+    std::lock_guard<std::mutex> lk(slot_mu);
+    for (int k = 0; k < kSlots; ++k) {  // next slot in ring order that is not still waiting for its consumers to be enqueued
+      const int c = (next_slot + k) % kSlots;
+      if (!slot_open[c]) {
+        s = c;
+        break;
+      }
+    }
+    if (s < 0) return fail(KOCR_ERR_STATE, "staging ring exhausted: more than 8 calls staged and not yet released");
+    next_slot = (s + 1) % kSlots;
+    slot_open[s] = true;
+  }
+  cudaError_t e = cudaEventSynchronize(slot_ev[s]);  // recorded after the slot's last consumer: normally long complete
+  if (e != cudaSuccess) {
+    std::lock_guard<std::mutex> lk(slot_mu);
+    slot_open[s] = false;
+    return fail(KOCR_ERR_CUDA, cudaGetErrorString(e));
+  }
   *h_out = h_slot[s];
   *slot = s;
   return KOCR_OK;
 }
 int Ctx::stage_commit(int s, size_t bytes, cudaStream_t stream, void** d_out) {
-  KOCR_CUDA_CHECK(cudaMemcpyAsync(d_slot[s], h_slot[s], bytes, cudaMemcpyHostToDevice, stream));
-  KOCR_CUDA_CHECK(cudaEventRecord(slot_ev[s], stream));
+  cudaError_t e = cudaMemcpyAsync(d_slot[s], h_slot[s], bytes, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) {
+    stage_release(s, stream);
+    return fail(KOCR_ERR_CUDA, cudaGetErrorString(e));
+  }
   *d_out = d_slot[s];
   return KOCR_OK;
 }
-int Ctx::stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out) {
+void Ctx::stage_release(int s, cudaStream_t stream) {
+  if (s < 0 || s >= kSlots) return;
+  cudaEventRecord(slot_ev[s], stream);
+  std::lock_guard<std::mutex> lk(slot_mu);
+  slot_open[s] = false;
+}
+int Ctx::stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out, int* slot_out) {
   void* h;
   int s;
   int rc = stage_begin(bytes, &h, &s);
   if (rc) return rc;
   memcpy(h, src, bytes);
-  return stage_commit(s, bytes, stream, d_out);
+  rc = stage_commit(s, bytes, stream, d_out);
+  if (rc) return rc;
+  if (slot_out) *slot_out = s;       // the caller releases it after enqueueing the consumers (StageGuard)
+  else stage_release(s, stream);     // no consumer beyond the copy itself
+  return KOCR_OK;
+}
+int Ctx::opt_in_smem(const void* func, int bytes) {
+  std::lock_guard<std::mutex> lk(attr_mu);
+  if (smem_attr_done.count(func)) return KOCR_OK;
+  KOCR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  smem_attr_done.insert(func);
+  return KOCR_OK;
 }
 
 cudaEvent_t Ctx::prof_event() {

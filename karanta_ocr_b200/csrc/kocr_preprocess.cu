@@ -376,6 +376,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   int slot;
   int rc = ctx->stage_begin(total, &h, &slot);
   if (rc) return rc;
+  StageGuard guard(ctx, slot, stream);  // released after preprocess_kernel (the tables' only reader) is enqueued
   uint8_t* hb = static_cast<uint8_t*>(h);
   uint8_t* db = static_cast<uint8_t*>(ctx->d_slot[slot]);
   for (auto& kv : needs) {
@@ -398,7 +399,10 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   memcpy(hb + jobs_off, jobs.data(), sizeof(PageJob) * n_images);
   void* d;
   rc = ctx->stage_commit(slot, total, stream, &d);
-  if (rc) return rc;
+  if (rc) {
+    guard.slot = -1;  // stage_commit released it
+    return rc;
+  }
 
   int max_coef = 0;
   for (int i = 0; i < n_images; ++i)
@@ -423,11 +427,11 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
   ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<true>), 220 * 1024))) return rc;
     preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
                                                               pixel_values, max_mid, coef_off, out_off);
   } else {
-    KOCR_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<false>), 220 * 1024))) return rc;
     preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
                                                                pixel_values, max_mid, coef_off, out_off);
   }

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -26,8 +27,28 @@ struct BlockW {
   float *c1_qkv = nullptr, *c1_fc1 = nullptr;  // row sums of the gamma-scaled weights (norm1 -> qkv, norm2 -> fc1 folding)
 };
 
+// Per-grid plan ("kocr_plan"): everything kocr_tower_forward derives from grid_thw alone - patch
+// positions, the attention work lists, the window permutation and per-row window bounds - built once on the host, kept in
+// HBM and reused by every later forward with the same grid_thw (a serving loop sees the same page shape again and again).
+struct Plan {
+  std::vector<int64_t> key;  // grid_thw, flattened
+  uint8_t* d = nullptr;      // device tables
+  size_t cap = 0;            // bytes allocated at d
+  size_t off_pos = 0, off_wf = 0, off_ww = 0, off_wi = 0, off_rw = 0;
+  int S = 0, max_pos = 0, n_work_full = 0, n_work_win = 0;
+  cudaEvent_t used = nullptr;       // recorded after the last forward that reads the tables was enqueued
+  cudaStream_t last_stream = nullptr;
+  bool multi_stream = false;
+  uint64_t tick = 0;
+};
+
 struct Tower {
   Ctx* ctx = nullptr;
+  static constexpr int kMaxPlans = 16;
+  std::vector<Plan*> plans;
+  std::mutex plan_mu;
+  uint64_t plan_tick = 0;
+  int64_t plan_hits = 0, plan_misses = 0;
   KocrTowerConfig cfg{};
   int D = 0, H = 0, F = 0, Fp = 0, O = 0, PD = 0, m2 = 4;
   bool q25 = false;
@@ -111,6 +132,103 @@ static WsLayout ws_layout(const Tower& t, int64_t S, bool need_pv) {
   return w;
 }
 
+// Look the plan up by grid_thw or build it: host planning + one H2D copy through the pinned staging ring.
+static int get_plan(Tower* t, const int64_t* grid_thw, int n_images, cudaStream_t st, Plan** out) {
+  Ctx* ctx = t->ctx;
+  std::lock_guard<std::mutex> lk(t->plan_mu);
+  const size_t nk = (size_t)n_images * 3;
+  for (Plan* p : t->plans)
+    if (p->key.size() == nk && memcmp(p->key.data(), grid_thw, nk * sizeof(int64_t)) == 0) {
+      p->tick = ++t->plan_tick;
+      ++t->plan_hits;
+      *out = p;
+      return KOCR_OK;
+    }
+  ++t->plan_misses;
+  int64_t S64 = 0;
+  int max_pos = 0, n_seq_max = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const int64_t tt = grid_thw[3 * i], h = grid_thw[3 * i + 1], w = grid_thw[3 * i + 2];
+    if (tt <= 0 || h <= 0 || w <= 0 || h % 2 || w % 2) return fail(KOCR_ERR_INVALID, "kocr_tower_forward: bad grid_thw");
+    S64 += tt * h * w;
+    max_pos = std::max<int>(max_pos, (int)std::max(h, w));
+    n_seq_max += (int)tt;
+  }
+  if (S64 > (int64_t)1 << 30) return fail(KOCR_ERR_UNSUPPORTED, "kocr_tower_forward: batch too large, split it");
+  const int S = (int)S64;
+  int rc;
+  std::vector<int32_t> pos((size_t)S * 2), cu(n_seq_max + 1);
+  int n_cu = 0;
+  if ((rc = pos_ids(grid_thw, n_images, 2, pos.data()))) return rc;
+  if ((rc = cu_seqlens(grid_thw, n_images, cu.data(), &n_cu))) return rc;
+  std::vector<int32_t> widx, cuw;
+  int n_cuw = 0;
+  if (t->q25) {
+    widx.resize(S / 4);
+    cuw.resize(S / 4 + 2);
+    if ((rc = window_index(grid_thw, n_images, t->cfg.window_size, 2, t->cfg.patch_size, widx.data(), cuw.data(), &n_cuw)))
+      return rc;
+    std::vector<int32_t> p2(pos.size());
+    for (int g = 0; g < S / 4; ++g) memcpy(&p2[(size_t)g * 8], &pos[(size_t)widx[g] * 8], 8 * sizeof(int32_t));
+    pos.swap(p2);
+  }
+  std::vector<AttnWork> work_full, work_win;
+  if ((rc = build_attn_work(cu.data(), n_cu - 1, &work_full))) return rc;
+  std::vector<int32_t> row_win;
+  if (t->q25 && (rc = build_attn_work_windowed(cu.data(), n_cu - 1, cuw.data(), n_cuw - 1, &work_win, &row_win))) return rc;
+
+  const size_t off_pos = 0;
+  const size_t off_wf = align256(pos.size() * 4);
+  const size_t off_ww = off_wf + align256(work_full.size() * sizeof(AttnWork));
+  const size_t off_wi = off_ww + align256(work_win.size() * sizeof(AttnWork));
+  const size_t off_rw = off_wi + align256(widx.size() * 4);
+  const size_t total = off_rw + align256(row_win.size() * 4);
+
+  // a plan object: a fresh one while the cache has room, else the least recently used one (its buffer is reused when it
+  // is large enough, so a stream of ever-changing batches settles into no allocation at all)
+  Plan* p = nullptr;
+  if ((int)t->plans.size() < Tower::kMaxPlans) {
+    p = new Plan();
+    KOCR_CUDA_CHECK(cudaEventCreateWithFlags(&p->used, cudaEventDisableTiming));
+    t->plans.push_back(p);
+  } else {
+    p = *std::min_element(t->plans.begin(), t->plans.end(), [](const Plan* a, const Plan* b) { return a->tick < b->tick; });
+    if (p->multi_stream) KOCR_CUDA_CHECK(cudaDeviceSynchronize());
+    else KOCR_CUDA_CHECK(cudaEventSynchronize(p->used));  // ~16 forwards old: normally long complete
+  }
+  p->key.clear();  // invalid until the tables are in place
+  if (p->cap < total) {
+    if (p->d) cudaFree(p->d);
+    p->d = nullptr;
+    p->cap = 0;
+    const size_t cap = std::max<size_t>(align256(total + total / 4), 1 << 16);
+    KOCR_CUDA_CHECK(cudaMalloc(&p->d, cap));
+    p->cap = cap;
+  }
+  void* hs;
+  int slot;
+  if ((rc = ctx->stage_begin(total, &hs, &slot))) return rc;
+  uint8_t* hb = static_cast<uint8_t*>(hs);
+  memcpy(hb + off_pos, pos.data(), pos.size() * 4);
+  memcpy(hb + off_wf, work_full.data(), work_full.size() * sizeof(AttnWork));
+  if (!work_win.empty()) memcpy(hb + off_ww, work_win.data(), work_win.size() * sizeof(AttnWork));
+  if (!widx.empty()) memcpy(hb + off_wi, widx.data(), widx.size() * 4);
+  if (!row_win.empty()) memcpy(hb + off_rw, row_win.data(), row_win.size() * 4);
+  cudaError_t e = cudaMemcpyAsync(p->d, hs, total, cudaMemcpyHostToDevice, st);
+  ctx->stage_release(slot, st);  // the pinned slot's only reader is this copy
+  if (e != cudaSuccess) return fail(KOCR_ERR_CUDA, cudaGetErrorString(e));
+  p->off_pos = off_pos; p->off_wf = off_wf; p->off_ww = off_ww; p->off_wi = off_wi; p->off_rw = off_rw;
+  p->S = S; p->max_pos = max_pos; p->n_work_full = (int)work_full.size(); p->n_work_win = (int)work_win.size();
+  p->last_stream = st;
+  p->multi_stream = false;
+  p->tick = ++t->plan_tick;
+  p->key.assign(grid_thw, grid_thw + nk);
+  // other streams must not read the tables before the copy lands: they wait on `used`, which is (re)recorded here
+  cudaEventRecord(p->used, st);
+  *out = p;
+  return KOCR_OK;
+}
+
 }  // namespace kocr
 
 using namespace kocr;
@@ -188,8 +306,14 @@ void kocr_tower_destroy(KocrTower* tower) {
   if (!tower) return;
   Tower* t = reinterpret_cast<Tower*>(tower);
   cudaSetDevice(t->ctx->device);
+  cudaDeviceSynchronize();
   for (void* p : t->allocs) cudaFree(p);
   if (t->rope_cs) cudaFree(t->rope_cs);
+  for (Plan* p : t->plans) {
+    if (p->d) cudaFree(p->d);
+    if (p->used) cudaEventDestroy(p->used);
+    delete p;
+  }
   delete t;
 }
 
@@ -319,6 +443,14 @@ int64_t kocr_tower_workspace_bytes(const KocrTower* tower, const int64_t* grid_t
   return (int64_t)ws_layout(*t, S, true).total;
 }
 
+int kocr_tower_plan_stats(const KocrTower* tower, int64_t* hits, int64_t* misses) {
+  const Tower* t = reinterpret_cast<const Tower*>(tower);
+  if (!t || !hits || !misses) return fail(KOCR_ERR_INVALID, "kocr_tower_plan_stats: null argument");
+  *hits = t->plan_hits;
+  *misses = t->plan_misses;
+  return KOCR_OK;
+}
+
 int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype, const int64_t* grid_thw, int n_images,
                        void* out, void* hidden_out, void* workspace, int64_t workspace_bytes, void* stream_) {
   Tower* t = reinterpret_cast<Tower*>(tower);
@@ -333,18 +465,20 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   Ctx* ctx = t->ctx;
   const int D = t->D, H = t->H, Fp = t->Fp, O = t->O;
 
-  // ---- host planning: positions, sequences, windows
-  int64_t S64 = 0;
-  int max_pos = 0, n_seq_max = 0;
-  for (int i = 0; i < n_images; ++i) {
-    const int64_t tt = grid_thw[3 * i], h = grid_thw[3 * i + 1], w = grid_thw[3 * i + 2];
-    if (tt <= 0 || h <= 0 || w <= 0 || h % 2 || w % 2) return fail(KOCR_ERR_INVALID, "kocr_tower_forward: bad grid_thw");
-    S64 += tt * h * w;
-    max_pos = std::max<int>(max_pos, (int)std::max(h, w));
-    n_seq_max += (int)tt;
+  // ---- plan: positions, sequences, windows (cached per grid_thw)
+  KOCR_CUDA_CHECK(cudaSetDevice(ctx->device));
+  Plan* plan = nullptr;
+  if ((rc = get_plan(t, grid_thw, n_images, st, &plan))) return rc;
+  if (plan->last_stream != st) {  // built or last used on another stream: order this stream after it
+    KOCR_CUDA_CHECK(cudaStreamWaitEvent(st, plan->used, 0));
+    plan->multi_stream = true;
+    plan->last_stream = st;
   }
-  if (S64 > (int64_t)1 << 30) return fail(KOCR_ERR_UNSUPPORTED, "kocr_tower_forward: batch too large, split it");
-  const int S = (int)S64;
+  struct PlanUse {  // the tables stay alive (not evicted / overwritten) until every forward that reads them has run
+    Plan* p; cudaStream_t s;
+    ~PlanUse() { cudaEventRecord(p->used, s); }
+  } plan_use{plan, st};
+  const int S = plan->S, max_pos = plan->max_pos;
   const WsLayout wl = ws_layout(*t, S, pv_dtype == KOCR_DTYPE_F32);
   if ((int64_t)wl.total > workspace_bytes) return fail(KOCR_ERR_INVALID, "kocr_tower_forward: workspace too small");
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
@@ -359,59 +493,25 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   auto* st_tmp = reinterpret_cast<float2*>(ws + wl.st_tmp);
   const int slots = t->stat_slots;
 
-  if (max_pos > t->rope_max_pos) {  // grow the (cos, sin) table; rare
-    KOCR_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (max_pos > t->rope_max_pos) {  // grow the (cos, sin) table; rare. Forwards on other streams may still read the old
+    KOCR_CUDA_CHECK(cudaDeviceSynchronize());  // table, so the whole device is drained before it is freed
     if (t->rope_cs) cudaFree(t->rope_cs);
-    t->rope_max_pos = std::max(max_pos, 256);
-    KOCR_CUDA_CHECK(cudaMalloc(&t->rope_cs, (size_t)t->rope_max_pos * 20 * sizeof(float2)));
-    rc = launch_rope_table(t->rope_cs, t->rope_max_pos, 20, 10000.0f, st);
+    t->rope_cs = nullptr;
+    const int grown = std::max(max_pos, 256);
+    KOCR_CUDA_CHECK(cudaMalloc(&t->rope_cs, (size_t)grown * 20 * sizeof(float2)));
+    rc = launch_rope_table(t->rope_cs, grown, 20, 10000.0f, st);
     if (rc) return rc;
+    KOCR_CUDA_CHECK(cudaStreamSynchronize(st));  // complete before any other stream's forward can pick it up
+    t->rope_max_pos = grown;
   }
 
-  std::vector<int32_t> pos((size_t)S * 2), cu(n_seq_max + 1);
-  int n_cu = 0;
-  if ((rc = pos_ids(grid_thw, n_images, 2, pos.data()))) return rc;
-  if ((rc = cu_seqlens(grid_thw, n_images, cu.data(), &n_cu))) return rc;
-  std::vector<int32_t> widx, cuw;
-  int n_cuw = 0;
-  if (t->q25) {
-    widx.resize(S / 4);
-    cuw.resize(S / 4 + 2);
-    if ((rc = window_index(grid_thw, n_images, t->cfg.window_size, 2, t->cfg.patch_size, widx.data(), cuw.data(), &n_cuw)))
-      return rc;
-    std::vector<int32_t> p2(pos.size());
-    for (int g = 0; g < S / 4; ++g) memcpy(&p2[(size_t)g * 8], &pos[(size_t)widx[g] * 8], 8 * sizeof(int32_t));
-    pos.swap(p2);
-  }
-  std::vector<AttnWork> work_full, work_win;
-  if ((rc = build_attn_work(cu.data(), n_cu - 1, &work_full))) return rc;
-  std::vector<int32_t> row_win;
-  if (t->q25 && (rc = build_attn_work_windowed(cu.data(), n_cu - 1, cuw.data(), n_cuw - 1, &work_win, &row_win))) return rc;
-
-  // ---- stage the tables
-  const size_t off_pos = 0;
-  const size_t off_wf = align256(pos.size() * 4);
-  const size_t off_ww = off_wf + align256(work_full.size() * sizeof(AttnWork));
-  const size_t off_wi = off_ww + align256(work_win.size() * sizeof(AttnWork));
-  const size_t off_rw = off_wi + align256(widx.size() * 4);
-  const size_t total = off_rw + align256(row_win.size() * 4);
-  void* hs;
-  int slot;
-  if ((rc = ctx->stage_begin(total, &hs, &slot))) return rc;
-  uint8_t* hb = static_cast<uint8_t*>(hs);
-  memcpy(hb + off_pos, pos.data(), pos.size() * 4);
-  memcpy(hb + off_wf, work_full.data(), work_full.size() * sizeof(AttnWork));
-  if (!work_win.empty()) memcpy(hb + off_ww, work_win.data(), work_win.size() * sizeof(AttnWork));
-  if (!widx.empty()) memcpy(hb + off_wi, widx.data(), widx.size() * 4);
-  if (!row_win.empty()) memcpy(hb + off_rw, row_win.data(), row_win.size() * 4);
-  void* ds;
-  if ((rc = ctx->stage_commit(slot, total, st, &ds))) return rc;
-  uint8_t* db = static_cast<uint8_t*>(ds);
-  const int2* d_pos = reinterpret_cast<const int2*>(db + off_pos);
-  const AttnWork* d_wf = reinterpret_cast<const AttnWork*>(db + off_wf);
-  const AttnWork* d_ww = reinterpret_cast<const AttnWork*>(db + off_ww);
-  const int32_t* d_wi = reinterpret_cast<const int32_t*>(db + off_wi);
-  const int2* d_rw = reinterpret_cast<const int2*>(db + off_rw);
+  const uint8_t* db = plan->d;
+  const int2* d_pos = reinterpret_cast<const int2*>(db + plan->off_pos);
+  const AttnWork* d_wf = reinterpret_cast<const AttnWork*>(db + plan->off_wf);
+  const AttnWork* d_ww = reinterpret_cast<const AttnWork*>(db + plan->off_ww);
+  const int32_t* d_wi = reinterpret_cast<const int32_t*>(db + plan->off_wi);
+  const int2* d_rw = reinterpret_cast<const int2*>(db + plan->off_rw);
+  const int n_work_full = plan->n_work_full, n_work_win = plan->n_work_win;
 
   // ---- patch embed (HF :304-310; Conv3d with kernel == stride is a GEMM over the flattened patch)
   const void* pv = pixel_values;
@@ -454,8 +554,8 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
     }
     {
       ProfScope ps(ctx, kProfAttention, st);
-      if (full) rc = launch_attention(ctx, qkv, attn, d_wf, (int)work_full.size(), H, S, st);
-      else rc = launch_attention(ctx, qkv, attn, d_ww, (int)work_win.size(), H, S, st, d_rw);
+      if (full) rc = launch_attention(ctx, qkv, attn, d_wf, n_work_full, H, S, st);
+      else rc = launch_attention(ctx, qkv, attn, d_ww, n_work_win, H, S, st, d_rw);
       if (rc) return rc;
     }
     GemmEpilogue e2{};

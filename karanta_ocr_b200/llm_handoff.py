@@ -18,9 +18,22 @@ from . import _lib
 IMAGE_TOKEN_ID = 151655  # Qwen2VLConfig.image_token_id
 
 
+VISION_START_TOKEN_ID = 151652  # Qwen2VLConfig.vision_start_token_id
+
+
 def get_rope_index(input_ids, image_grid_thw=None, attention_mask=None, image_token_id: int = IMAGE_TOKEN_ID,
-                   spatial_merge_size: int = 2):
-    """-> (position_ids int64 [3, batch, seq_len], mrope_position_deltas int64 [batch, 1]) on the CPU."""
+                   spatial_merge_size: int = 2, semantics: str = "5.x", vision_start_token_id: int | None = VISION_START_TOKEN_ID):
+    """-> (position_ids int64 [3, batch, seq_len], mrope_position_deltas int64 [batch, 1]) on the CPU.
+
+    `semantics` picks the transformers line to reproduce. "5.x" (default) is what the build image runs and what
+    tests/golden/g6_llm_handoff.npz pins: padded positions are 0 and delta = max + 1 - (unmasked length). "4.5x" is the line
+    karanta-ocr pins (4.53.3, /root/reference/uv.lock:2168-2169): padded positions are 1, delta = max + 1 - (padded length) -
+    the value generate() adds to cache_position, so left-padded batches decode at the positions that stack expects - and
+    images are located by <|vision_start|> (vision_start_token_id=None: by runs of image tokens) and consume exactly their
+    grid's token count, so adjacent images need no separator. The 4.5x mode is restated from its source and has no golden here
+    (that version is not installed offline): use it when the surrounding model code is transformers 4.5x."""
+    if semantics not in ("5.x", "4.5x"):
+        raise ValueError("semantics must be '5.x' or '4.5x'")
     ids = np.ascontiguousarray(torch.as_tensor(input_ids).detach().cpu().numpy().astype(np.int64))
     if ids.ndim != 2:
         raise ValueError("input_ids must be [batch, seq_len]")
@@ -34,9 +47,11 @@ def get_rope_index(input_ids, image_grid_thw=None, attention_mask=None, image_to
         torch.as_tensor(image_grid_thw).detach().cpu().numpy().astype(np.int64).reshape(-1, 3))
     pos = np.zeros((3, B, L), dtype=np.int64)
     deltas = np.zeros((B,), dtype=np.int64)
-    rc = _lib.load().kocr_mrope_position_ids(ids.ctypes.data, mask.ctypes.data if mask is not None else None, B, L,
-                                             grid.ctypes.data if len(grid) else None, len(grid), int(image_token_id),
-                                             int(spatial_merge_size), pos.ctypes.data, deltas.ctypes.data)
+    rc = _lib.load().kocr_mrope_position_ids_v2(ids.ctypes.data, mask.ctypes.data if mask is not None else None, B, L,
+                                                grid.ctypes.data if len(grid) else None, len(grid), int(image_token_id),
+                                                -1 if vision_start_token_id is None else int(vision_start_token_id),
+                                                int(spatial_merge_size), 0 if semantics == "5.x" else 1, pos.ctypes.data,
+                                                deltas.ctypes.data)
     _lib.check(rc)
     return torch.from_numpy(pos), torch.from_numpy(deltas).unsqueeze(1)
 

@@ -99,3 +99,71 @@ def test_bad_page_fails_its_task_not_the_job(tmp_path):
     assert s["failed"] == 2 and s["completed"] == 0
     rec = json.load(open(tmp_path / "job" / "results" / "doc0.pdf-1.json"))
     assert "aspect ratio" in rec["error"]
+
+
+def test_one_bad_page_in_a_batch_fails_alone(tmp_path):
+    """a corrupt PNG, an unencodable page and a hostile custom_id each fail their own task; the other
+    pages of the same batch are encoded, nothing is double counted and nothing is written outside out_dir."""
+    pages = [synth_page(56, 56, 1), synth_page(84, 56, 2), synth_page(56, 84, 3), synth_page(112, 56, 4)]
+    path = make_requests(tmp_path, pages)
+    lines = open(path).read().splitlines()
+    rec = json.loads(lines[1])                                   # page 1: not an image at all
+    body = rec.get("body", rec)
+    body["messages"][0]["content"][1]["image_url"]["url"] = "data:image/png;base64," + base64.b64encode(b"not a png").decode()
+    lines[1] = json.dumps(rec)
+    rec = json.loads(lines[3])                                   # page 3: a path as custom_id
+    rec["custom_id"] = "../../escape"
+    lines[3] = json.dumps(rec)
+    open(path, "w").write("\n".join(lines) + "\n")
+
+    class Picky(FakeEncoder):
+        def encode_to_host(self, pages):
+            if any(p.size == (84, 56) for p in pages):       # page 2 (56 rows x 84 columns) cannot be encoded
+                raise ValueError("absolute aspect ratio must be smaller than 200")
+            return super().encode_to_host(pages)
+    out = tmp_path / "job"
+    s = bulk.run_encode_job(path, str(out), Picky(), batch_pages=4)
+    assert (s["completed"], s["failed"], s["skipped"]) == (1, 3, 0)
+    assert "result" in json.load(open(out / "results" / "doc0.pdf-1.json"))
+    assert "error" in json.load(open(out / "results" / "doc1.pdf-2.json"))
+    assert "aspect ratio" in json.load(open(out / "results" / "doc2.pdf-3.json"))["error"]
+    assert not (tmp_path / "escape.json").exists() and not (tmp_path.parent / "escape.json").exists()
+    bad = [f for f in (out / "results").iterdir() if f.name.startswith("invalid_id_")]
+    assert len(bad) == 1 and json.load(open(bad[0]))["task_id"] == "../../escape"
+    with pytest.raises(ValueError):
+        bulk.safe_task_id("a/b")
+    with pytest.raises(ValueError):
+        bulk.safe_task_id(".hidden")
+
+
+def test_resume_skips_finished_tasks_and_keeps_state_in_sqlite(tmp_path):
+    """bulk_processing/workers/inference_worker.py:315-321 (skip when the result file exists) and
+    bulk_processing/utils/database.py:16-49,201-222 (job / task tables, pending = pending or retryable failed)."""
+    import sqlite3
+    pages = [synth_page(56, 56, 1), synth_page(84, 56, 2), synth_page(56, 84, 3)]
+    path = make_requests(tmp_path, pages)
+    out, db = tmp_path / "job", str(tmp_path / "state.db")
+
+    class FailsOnce(FakeEncoder):
+        armed = True
+
+        def encode_to_host(self, pages):
+            if FailsOnce.armed and any(p.size == (84, 56) for p in pages):
+                raise RuntimeError("transient")
+            return super().encode_to_host(pages)
+    s1 = bulk.run_encode_job(path, str(out), FailsOnce(), batch_pages=2, state_db=db, job_id="job1")
+    assert (s1["completed"], s1["failed"]) == (2, 1)
+    conn = sqlite3.connect(db)
+    assert dict(conn.execute("SELECT status, COUNT(*) FROM tasks GROUP BY status").fetchall()) == {"completed": 2, "failed": 1}
+    assert conn.execute("SELECT status, total_tasks, completed_tasks, failed_tasks FROM jobs").fetchone() == ("completed_with_errors", 3, 2, 1)
+    FailsOnce.armed = False
+    enc = FailsOnce()
+    s2 = bulk.run_encode_job(path, str(out), enc, batch_pages=2, state_db=db, job_id="job1")
+    assert (s2["completed"], s2["failed"], s2["skipped"]) == (1, 0, 2) and len(enc.seen) == 1   # only the failed page ran again
+    assert conn.execute("SELECT status, completed_tasks, failed_tasks FROM jobs").fetchone() == ("completed", 3, 0)
+    assert conn.execute("SELECT attempts FROM tasks WHERE task_id = 'doc2.pdf-3'").fetchone() == (2,)
+    # without a database the result files alone make the job resumable
+    s3 = bulk.run_encode_job(path, str(out), FakeEncoder(), batch_pages=2)
+    assert (s3["completed"], s3["skipped"]) == (0, 3)
+    s4 = bulk.run_encode_job(path, str(out), FakeEncoder(), batch_pages=2, resume=False)
+    assert (s4["completed"], s4["skipped"]) == (3, 0)

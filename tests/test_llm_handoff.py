@@ -94,3 +94,51 @@ def test_scatter_full_page_batch():
     out = scatter_image_features(emb, ids, img, IMG)
     assert torch.equal(out[:, 20:20 + T].reshape(B * T, H), img)
     assert (out[:, :20] == 0).all() and (out[:, 20 + T:] == 0).all()
+
+
+def test_g6_golden_is_reproducible_from_transformers():
+    """tests/golden/make_golden.py g6 (the prompts are written out in the script) run live against the installed
+    transformers: the committed position ids / deltas are what Qwen2VLModel.get_rope_index returns for these prompts."""
+    pytest.importorskip("transformers")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(G, "g6_llm_handoff.npz"))
+    assert sorted(mg.G6_PROMPTS) == sorted({k.split(".")[0] for k in z.files if "." in k})
+    for name in mg.G6_PROMPTS:
+        pos, delta = mg._hf_rope_index(z[f"{name}.input_ids"], z[f"{name}.grid"], z[f"{name}.attention_mask"], mg.IMG_TOKEN)
+        assert np.array_equal(pos, z[f"{name}.position_ids"]) and np.array_equal(delta, z[f"{name}.deltas"]), name
+
+
+def test_position_ids_transformers_4_5x_semantics():
+    """The line the reference pins (transformers 4.53.3) differs from 5.x only at padding and at image location
+    (ADVICE round 1): padded positions hold 1, delta is taken against the padded length, adjacent images are split by
+    grid size. Unpadded single-image prompts must agree between the two modes."""
+    IMG, VS = 151655, 151652
+    z = np.load(os.path.join(G, "g6_llm_handoff.npz"))
+    # unpadded, one image, no <|vision_start|> in the golden prompts -> locate by runs: identical to 5.x
+    for n in ("one_page", "image_first"):
+        p5, d5 = get_rope_index(z[f"{n}.input_ids"], z[f"{n}.grid"], z[f"{n}.attention_mask"], image_token_id=IMG)
+        p4, d4 = get_rope_index(z[f"{n}.input_ids"], z[f"{n}.grid"], z[f"{n}.attention_mask"], image_token_id=IMG, semantics="4.5x",
+                                vision_start_token_id=None)
+        assert torch.equal(p4, p5) and torch.equal(d4, d5), n
+    # left-padded batch: pads are 1 and delta shrinks by the pad count
+    ids, mask, grid = z["batch_padded.input_ids"], z["batch_padded.attention_mask"], z["batch_padded.grid"]
+    p5, d5 = get_rope_index(ids, grid, mask, image_token_id=IMG)
+    p4, d4 = get_rope_index(ids, grid, mask, image_token_id=IMG, semantics="4.5x", vision_start_token_id=None)
+    m = torch.from_numpy(mask).bool()
+    assert torch.equal(p4[:, m], p5[:, m]) and (p4[:, ~m] == 1).all() and (p5[:, ~m] == 0).all()
+    pads = torch.from_numpy((mask == 0).sum(-1, keepdims=True))
+    assert torch.equal(d4, d5 - pads)
+    # <|vision_start|> locates the images; two images back to back are split by their grids (5.x refuses the merged run)
+    row = [7, VS] + [IMG] * 4 + [IMG] * 6 + [9]
+    with pytest.raises(ValueError):
+        get_rope_index(np.asarray([row]), [[1, 4, 4], [1, 4, 6]], None, image_token_id=IMG)
+    row = [7, VS] + [IMG] * 4 + [VS] + [IMG] * 6 + [9]
+    p4, d4 = get_rope_index(np.asarray([row]), [[1, 4, 4], [1, 4, 6]], None, image_token_id=IMG, semantics="4.5x")
+    p5, d5 = get_rope_index(np.asarray([row]), [[1, 4, 4], [1, 4, 6]], None, image_token_id=IMG)
+    assert torch.equal(p4, p5) and torch.equal(d4, d5)
+    # an image token that no <|vision_start|> announces is text in 4.5x
+    p4, _ = get_rope_index(np.asarray([[5, IMG, 6]]), None, None, image_token_id=IMG, semantics="4.5x")
+    assert p4[:, 0].tolist() == [[0, 1, 2]] * 3
