@@ -169,6 +169,32 @@ KOCR_API int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int 
  * and monitoring: forwards served from a cached plan / forwards that had to plan. */
 KOCR_API int kocr_tower_plan_stats(const KocrTower* tower, int64_t* hits, int64_t* misses);
 
+/* ------------------------------------------------------------------ page decode on the GPU */
+
+/* Stands in for the host decode in front of the path: PIL.Image.open(BytesIO(base64.b64decode(...))) on the PNG pages the
+ * reference passes around (karanta/data/utils.py:186-225 base64_to_grayscale and :228-251 prepare_image_and_text;
+ * karanta/data/process_pdf_utils.py:50-75 render_pdf_to_base64png; karanta/pipeline.py:131-142), i.e. libpng + zlib. */
+typedef struct KocrPngInfo {
+  int32_t height, width;
+  int32_t channels;      /* of the decoded page: 1 (gray, LAYOUT_GRAY) or 3 (RGB, LAYOUT_HWC); alpha is dropped like .convert() */
+  int32_t src_channels;  /* samples per pixel in the file: 1, 2 (gray+alpha), 3, 4 (RGBA) */
+  int32_t bit_depth, color_type, interlace;
+  int32_t reserved;
+  int64_t idat_bytes;    /* compressed payload */
+  int64_t raw_bytes;     /* filtered scan lines = height * (1 + width * src_channels) */
+} KocrPngInfo;
+
+/* Host only: walk the container (signature, IHDR, IDAT..., IEND; chunk CRCs checked).  KOCR_ERR_INVALID for a damaged file,
+ * KOCR_ERR_UNSUPPORTED for PNG flavours the kernels do not decode (palette, 16-bit, interlaced): decode those on the host. */
+KOCR_API int kocr_png_info(const uint8_t* file, int64_t size, KocrPngInfo* info);
+KOCR_API int64_t kocr_png_scratch_bytes(const KocrPngInfo* infos, int n);
+/* files: HOST pointers to n whole PNG files; out_dev[i]: DEVICE buffer of height*width*channels bytes ([H][W][C], C = 1 or 3),
+ * ready to be handed to kocr_preprocess as KOCR_LAYOUT_GRAY / KOCR_LAYOUT_HWC; scratch: DEVICE, kocr_png_scratch_bytes;
+ * status_dev: DEVICE int32[n], 0 = decoded, else which stream check failed (read it after synchronising the stream).
+ * Enqueues one H2D copy of the compressed bytes, inflate_kernel and unfilter_kernel on `stream`. */
+KOCR_API int kocr_png_decode(KocrCtx* ctx, const uint8_t* const* files, const int64_t* sizes, int n, void* const* out_dev,
+                             void* scratch, int64_t scratch_bytes, int32_t* status_dev, void* stream);
+
 /* ------------------------------------------------------------------ LLM hand-off */
 
 /* Host planning (no GPU): 3-D M-RoPE position ids of a text+image prompt.  Stands in for

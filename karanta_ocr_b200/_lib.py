@@ -29,6 +29,12 @@ class KocrTowerConfig(C.Structure):
 
 
 # name -> (restype, argtypes): every symbol include/kocr.h declares
+class KocrPngInfo(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32), ("src_channels", C.c_int32),
+                ("bit_depth", C.c_int32), ("color_type", C.c_int32), ("interlace", C.c_int32), ("reserved", C.c_int32),
+                ("idat_bytes", C.c_int64), ("raw_bytes", C.c_int64)]
+
+
 SIGNATURES = {
     "kocr_last_error": (C.c_char_p, []),
     "kocr_version": (C.c_char_p, []),
@@ -52,6 +58,10 @@ SIGNATURES = {
     "kocr_tower_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "kocr_tower_plan_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "kocr_png_info": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(KocrPngInfo)]),
+    "kocr_png_scratch_bytes": (C.c_int64, [C.POINTER(KocrPngInfo), C.c_int]),
+    "kocr_png_decode": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                  C.c_int64, C.c_void_p, C.c_void_p]),
     "kocr_mrope_position_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                           C.c_void_p]),
     "kocr_mrope_position_ids_v2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int,

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkocr.so")
 SOURCES = ["kocr_host.cu", "kocr_preprocess.cu", "kocr_elementwise.cu", "kocr_gemm.cu", "kocr_attention.cu",
-           "kocr_tower.cu", "kocr_handoff.cu"]
-HEADERS = ["kocr_common.cuh", "kocr_kernels.h", os.path.join("..", "..", "include", "kocr.h")]
+           "kocr_tower.cu", "kocr_handoff.cu", "kocr_png.cu"]
+HEADERS = ["kocr_common.cuh", "kocr_kernels.h", "kocr_inflate_core.h", os.path.join("..", "..", "include", "kocr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -9,8 +9,9 @@ batch variant nests the same thing under "body"). Pages are base64 PNG (grayscal
 Output: what `bulk_processing/workers/inference_worker.py:205-228` leaves behind - `results/<task_id>.json` with
 `{"task_id", "result", "timestamp"}` - where `result` points at the page's embedding file instead of generated text.
 
-Host side only: decoding is PIL on a thread pool (the reference decodes on the CPU too), the pages then go through
-PageEncoder (preprocess + tower on the GPU) in batches, sharded over ranks with shard_pages when world_size > 1.
+PNG pages are decoded on the GPU (inflate + scan-line filters in libkocr.so, row f2): the host only undoes the base64. JPEG and
+the PNG flavours the kernels do not take fall to Pillow on a thread pool, the reference's own decode. The pages then go
+through PageEncoder (preprocess + tower) in batches, sharded over ranks with shard_pages when world_size > 1.
 """
 from __future__ import annotations
 
@@ -155,7 +156,7 @@ def _result_done(path: str) -> bool:
 
 
 def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int = 64, rank: int = 0, world_size: int = 1,
-                   decode_threads: int | None = None, resume: bool = True, state_db: str | None = None, job_id: str | None = None,
+                   decode_threads: int | None = None, decode: str = "auto", resume: bool = True, state_db: str | None = None, job_id: str | None = None,
                    max_attempts: int = 3) -> dict:
     """Encode every page of `requests_jsonl` that falls in this rank's shard; write `<out_dir>/results/<task_id>.json` and
     `<out_dir>/embeddings/<task_id>.npy` (bf16 bit patterns as uint16, shape [tokens, out_hidden]). Returns a summary.
@@ -164,7 +165,9 @@ def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int 
     encoded (corrupt image, aspect ratio > 200, unusable custom_id) gets an `error` result file and the job goes on; when a
     whole batch fails on the GPU its pages are retried one by one to find the bad one. With `resume`, tasks whose result
     file already exists are skipped (inference_worker.py:315-321). With `state_db`, job / task state is kept in SQLite under
-    the reference's schema (bulk_processing/utils/database.py:16-49) and only pending / retryable tasks are run."""
+    the reference's schema (bulk_processing/utils/database.py:16-49) and only pending / retryable tasks are run.
+    `decode`: "gpu" = PNG pages go to the device undecoded, "host" = Pillow on the thread pool as the
+    reference does, "auto" = gpu when the encoder takes PNG bytes (PageEncoder does)."""
     import torch
     reqs = read_requests(requests_jsonl)
     res_dir, emb_dir = os.path.join(out_dir, "results"), os.path.join(out_dir, "embeddings")
@@ -173,7 +176,7 @@ def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int 
     minp, maxp = encoder.processor.min_pixels, encoder.processor.max_pixels
     pool = ThreadPoolExecutor(decode_threads or min(32, os.cpu_count() or 4))
     t0 = time.time()
-    counts = {"completed": 0, "failed": 0, "skipped": 0}
+    counts = {"completed": 0, "failed": 0, "skipped": 0, "gpu_decoded": 0}
     state = JobState(state_db, job_id or os.path.basename(requests_jsonl), {"requests": requests_jsonl, "batch_pages": batch_pages}) if state_db else None
     db_rows = []
 
@@ -229,8 +232,18 @@ def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int 
         state.update(db_rows)
     db_rows.clear()
 
-    def decode(i):
+    gpu_decode = decode == "gpu" or (decode == "auto" and getattr(encoder, "accepts_png_bytes", False))
+
+    def decode_page(i):
+        """GPU decode: hand the PNG file bytes through (base64 is undone here, inflate + unfilter run on the device). Anything
+        the device kernels do not take - JPEG, palette / 16-bit / interlaced PNG - is decoded by Pillow, as the reference does."""
         try:
+            if gpu_decode:
+                from .png_decode import is_gpu_decodable, payload_bytes
+                data = payload_bytes(reqs[i][1])
+                if is_gpu_decodable(data):
+                    counts["gpu_decoded"] += 1
+                    return data
             return decode_data_uri(reqs[i][1])
         except Exception as e:
             return e
@@ -256,11 +269,11 @@ def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int 
             db_rows.append((tid, "completed", None, ms))
 
     batches = [mine[b:b + batch_pages] for b in range(0, len(mine), batch_pages)]
-    nxt = pool.map(decode, batches[0]) if batches else None
+    nxt = pool.map(decode_page, batches[0]) if batches else None
     for bi, idx in enumerate(batches):
         decoded = list(nxt)
         if bi + 1 < len(batches):  # decode the next batch while this one is on the GPU
-            nxt = pool.map(decode, batches[bi + 1])
+            nxt = pool.map(decode_page, batches[bi + 1])
         if state:
             state.update([(names[i], "processing", None, None) for i in idx])
         good = [(i, p) for i, p in zip(idx, decoded) if not isinstance(p, Exception)]
@@ -287,7 +300,7 @@ def run_encode_job(requests_jsonl: str, out_dir: str, encoder, batch_pages: int 
         state.finish()
     dt = time.time() - t0
     return {"rank": rank, "world_size": world_size, "total_requests": len(reqs), "completed": counts["completed"], "failed": counts["failed"],
-            "skipped": counts["skipped"], "seconds": dt, "pages_per_s": counts["completed"] / dt if dt > 0 else None}
+            "skipped": counts["skipped"], "gpu_decoded_pages": counts["gpu_decoded"], "seconds": dt, "pages_per_s": counts["completed"] / dt if dt > 0 else None}
 
 
 def load_embedding(out_dir: str, task_id: str):

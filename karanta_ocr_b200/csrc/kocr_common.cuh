@@ -77,6 +77,11 @@ struct Ctx {
   std::mutex attr_mu;
   std::set<const void*> smem_attr_done;
   int opt_in_smem(const void* func, int bytes);
+  // pinned buffer for compressed PNG payloads on their way to the device (kocr_png_decode)
+  std::mutex png_mu;
+  void* png_pinned = nullptr;
+  size_t png_pinned_cap = 0;
+  cudaEvent_t png_pinned_ev = nullptr;
   // optional per-kernel-class timing with CUDA events on the launching stream (kocr_profile_begin / _end)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int cls; };

@@ -317,7 +317,11 @@ int Ctx::stage(const void* src, size_t bytes, cudaStream_t stream, void** d_out,
 int Ctx::opt_in_smem(const void* func, int bytes) {
   std::lock_guard<std::mutex> lk(attr_mu);
   if (smem_attr_done.count(func)) return KOCR_OK;
-  KOCR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // not sticky: do not let the next launch check report it
+    return fail(KOCR_ERR_CUDA, std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize, ") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  }
   smem_attr_done.insert(func);
   return KOCR_OK;
 }
@@ -465,6 +469,8 @@ void kocr_destroy(KocrCtx* ctx) {
   }
   for (int mode = 0; mode < 2; ++mode)
     if (c->d_lut[mode]) cudaFree(c->d_lut[mode]);
+  if (c->png_pinned) cudaFreeHost(c->png_pinned);
+  if (c->png_pinned_ev) cudaEventDestroy(c->png_pinned_ev);
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   delete c;

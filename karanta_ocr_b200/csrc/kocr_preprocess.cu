@@ -40,6 +40,7 @@ static constexpr int kStrip = 28;       // output rows per tile = patch * merge
 static constexpr int kPatchDim = 1176;  // 3 * 2 * 14 * 14
 static constexpr int kThreads = 256;
 static constexpr int kMaxStageRows = 768;  // staged input rows per tile (3 planes x up to 256 rows)
+static constexpr int kMaxDynSmem = 208 * 1024;  // dynamic shared memory opt-in; + ~10 KB static (LUT, job, row pointers) <= 227 KB
 static constexpr int kRB = 14;           // rows of horizontal-pass accumulators held in registers per thread
 
 // 1-D bulk async copy shared -> global (TMA engine, no tensor map): size and both addresses multiples of 16 bytes
@@ -422,16 +423,16 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   }
   const int out_bytes = (max_tw / kStrip) * 4 * kPatchDim * (out_dtype == KOCR_DTYPE_BF16 ? 2 : 4);
   const int smem = out_off + std::max(out_bytes, stage_bytes);
-  if (smem > 220 * 1024) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: tile does not fit in shared memory");
+  if (smem > kMaxDynSmem) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: tile does not fit in shared memory");
   const int grid = std::min(tiles, ctx->num_sms * 8);
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
   ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
-    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<true>), 220 * 1024))) return rc;
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<true>), kMaxDynSmem))) return rc;
     preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
                                                               pixel_values, max_mid, coef_off, out_off);
   } else {
-    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<false>), 220 * 1024))) return rc;
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<false>), kMaxDynSmem))) return rc;
     preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
                                                                pixel_values, max_mid, coef_off, out_off);
   }

@@ -89,31 +89,59 @@ class PageEncoder:
             outs.extend(t.cpu() for t in self.tower.split_per_image(emb, grid))
         return outs, mine
 
+    accepts_png_bytes = True  # pages may be undecoded PNG files (bytes / data URIs): they are decoded on the GPU
+
+    def _decode_png_entries(self, pages, check: bool):
+        """Replace the entries of `pages` that are PNG files (bytes, or base64 / data-URI strings as the reference's requests
+        carry them) by device tensors decoded on the GPU. Returns (pages, kernels launched)."""
+        idx = [i for i, p in enumerate(pages) if isinstance(p, (bytes, bytearray, memoryview, str))]
+        if not idx:
+            return pages, 0
+        from .png_decode import PngError, decode_png_batch, payload_bytes
+        try:
+            dec = decode_png_batch([payload_bytes(pages[i]) for i in idx], device=self.tower.device, check=check)
+        except PngError as e:
+            raise PngError(idx[e.index], str(e).split(": ", 1)[-1]) from e
+        self.last_png_status = (idx, decode_png_batch.last_status)
+        pages = list(pages)
+        for i, t in zip(idx, dec):
+            pages[i] = t
+        return pages, 2
+
     @torch.no_grad()
     def encode(self, pages):
+        pages, n_dec = self._decode_png_entries(pages, check=True)
         pv, grid = self.processor.preprocess_device(pages, out_dtype=torch.bfloat16)
         emb = self.tower(pv, grid_thw=grid)
-        self.last_launch_count = 1 + self.tower.last_launch_count
+        self.last_launch_count = 1 + self.tower.last_launch_count + n_dec
         return emb, grid
+
+    def encode_png(self, files):
+        """PNG files -> embeddings with the decode on the GPU: only compressed bytes cross PCIe. Raises PngError (with the
+        page's index) for a page that cannot be decoded."""
+        return self.encode(list(files))
 
     @torch.no_grad()
     def encode_to_host_async(self, pages, out_host: torch.Tensor):
         """Pipelined end-to-end call for bulk encoding: the H2D copy + preprocess run on an input stream, the tower on the
         caller's stream, the D2H of the embeddings on an output stream, chained by events, so consecutive calls overlap
         their copies with each other's compute. Returns (event that completes when out_host is filled, grid, n_rows);
-        the caller must not reuse `out_host` (or its pages) before that event."""
+        the caller must not reuse `out_host` (or its pages) before that event. Pages given as PNG file bytes are decoded by
+        kernels on the input stream as well; after the event `last_png_status` = (their indices, int32 status tensor, 0 = ok)."""
         dev = self.tower.device
         if not hasattr(self, "_s_in"):
             self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(self._s_in):
+            # undecoded PNG files: inflate + unfilter on the input stream too, under the previous batch's tower
+            pages, n_dec = self._decode_png_entries(pages, check=False)
             pv, grid = self.processor.preprocess_device(pages, out_dtype=torch.bfloat16)
             ev_in = torch.cuda.Event()
             ev_in.record(self._s_in)
         cur.wait_event(ev_in)
         pv.record_stream(cur)
         emb = self.tower(pv, grid_thw=grid)
-        self.last_launch_count = 1 + self.tower.last_launch_count
+        self.last_launch_count = 1 + self.tower.last_launch_count + n_dec
         ev_c = torch.cuda.Event()
         ev_c.record(cur)
         self._s_out.wait_event(ev_c)

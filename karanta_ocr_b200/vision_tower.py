@@ -174,7 +174,9 @@ class KarantaVisionTower(torch.nn.Module):
                 self._ws = None
                 self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
             out = torch.empty((S // m2, self.cfg["out_hidden"]), dtype=torch.bfloat16, device=dev)
-            hid = torch.empty((S, self.cfg["embed_dim"]), dtype=torch.bfloat16, device=dev) if return_hidden else None
+            # 5.x callers get last_hidden_state filled like upstream's BaseModelOutputWithPooling (one extra D2D copy)
+            want_hidden = return_hidden or self.hf_output
+            hid = torch.empty((S, self.cfg["embed_dim"]), dtype=torch.bfloat16, device=dev) if want_hidden else None
             rc = _lib.load().kocr_tower_forward(self._h, x.data_ptr(), _DT[x.dtype], g.ctypes.data, g.shape[0], out.data_ptr(),
                                                 hid.data_ptr() if hid is not None else None, self._ws.data_ptr(),
                                                 self._ws.numel(), torch.cuda.current_stream(dev).cuda_stream)

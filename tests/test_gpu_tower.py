@@ -274,3 +274,67 @@ def test_norm_folding_with_outlier_channels(arch):
     assert (x0.mean(-1).abs() / x0.std(-1)).median() > 0.02 and x0.abs().max() > 50 * x0.abs().median()  # the regime is the intended one
     ref = vo.tower_forward(cfg, sd, torch.from_numpy(pv), gg)
     _check(emb, ref, gg, f"outliers_{arch}", _tau_from_oracle(cfg, sd, pv, gg, ref))
+
+
+def test_plan_is_cached_per_grid_and_reused_across_streams():
+    """SURVEY.md section 8 row B3 (`kocr_plan`): the tables derived from grid_thw are planned once per distinct grid and kept in
+    HBM; later forwards over the same grid (the serving loop) are bit-identical and do no planning, also from another
+    stream, and evicting the least recently used of 16 plans does not disturb results."""
+    import ctypes as C
+    from karanta_ocr_b200 import _lib
+    cfg = vo.TowerConfig("qwen2_5_vl", 2, 1280, 16, 3420, 1536, fullatt_block_indexes=(1,))
+    tower = _tower(cfg)
+
+    def stats():
+        h, m = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().kocr_tower_plan_stats(tower._h, C.byref(h), C.byref(m)))
+        return h.value, m.value
+    g = torch.Generator().manual_seed(3)
+    grid = [[1, 20, 18], [1, 8, 30]]
+    pv = torch.randn(20 * 18 + 8 * 30, 1176, generator=g).cuda()
+    a = tower(pv, grid_thw=grid)
+    assert stats() == (0, 1)
+    b = tower(pv, grid_thw=torch.tensor(grid))
+    assert stats() == (1, 1) and torch.equal(a, b)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        c = tower(pv, grid_thw=grid)
+    side.synchronize()
+    assert stats() == (2, 1) and torch.equal(a, c)
+    for k in range(20):   # more distinct grids than the cache holds
+        gk = [[1, 4 + 2 * k, 6]]
+        tower(torch.randn((4 + 2 * k) * 6, 1176, generator=g).cuda(), grid_thw=gk)
+    assert stats() == (2, 21)
+    d = tower(pv, grid_thw=grid)   # evicted meanwhile: planned again, same result
+    assert stats() == (2, 22) and torch.equal(a, d)
+
+
+def test_hf5_output_carries_last_hidden_state():
+    cfg = CASES["tiny_q2"]
+    from karanta_ocr_b200 import KarantaVisionTower
+    t = KarantaVisionTower(dict(arch="qwen2_vl", depth=2, embed_dim=160, num_heads=2, mlp_hidden=640, out_hidden=256), hf_output=True)
+    sd = vo.init_weights(cfg, seed=1)
+    t.load_state_dict(sd)
+    pv = torch.randn(48, 1176, generator=torch.Generator().manual_seed(1))
+    y = t(pv, grid_thw=[[1, 8, 6]])
+    ref, hid = vo.tower_forward(cfg, sd, pv, [[1, 8, 6]], return_hidden=True)
+    assert y.pooler_output.shape == (12, 256) and y.last_hidden_state.shape == (48, 160)
+    assert torch.nn.functional.cosine_similarity(y.last_hidden_state.float().cpu().flatten(), hid.flatten(), dim=0) > 0.999
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_devices_in_one_process():
+    """the >48 KB dynamic shared-memory opt-in is per device; a tower on a second GPU of the same process
+    and thread must launch its GEMM / attention kernels just the same."""
+    from karanta_ocr_b200 import KarantaVisionTower
+    cfg = CASES["mid_q2_d2"]
+    sd = vo.init_weights(cfg, seed=100)
+    pv = torch.randn(20 * 18, 1176, generator=torch.Generator().manual_seed(2))
+    outs = []
+    for dev in (0, 1):
+        t = KarantaVisionTower(dict(arch=cfg.arch, depth=cfg.depth, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
+                                    mlp_hidden=cfg.mlp_hidden, out_hidden=cfg.out_hidden), device=f"cuda:{dev}")
+        t.load_state_dict(sd)
+        outs.append(t(pv, grid_thw=[[1, 20, 18]]).cpu())
+    assert torch.equal(outs[0], outs[1])
