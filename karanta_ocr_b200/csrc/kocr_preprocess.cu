@@ -4,13 +4,22 @@
 // Stands in for Qwen2VLImageProcessor._preprocess (HF models/qwen2_vl/image_processing_qwen2_vl.py:148-232)
 // which the reference reaches from karanta/training/pipeline_steps.py:289-294.
 //
-// HBM-bound by design: each input byte is read ~once (plus the filter-support halo between strips),
-// each output element is written exactly once with fully coalesced 8-byte (f32) / 4-byte (bf16) stores.
-//   tile  = (page, strip of 28 output rows = one merge row, chunk of tile_w output columns)
-//   phase 1 horizontal taps from global (L1-resident rows) -> smem mid[3][rows_in][tile_w]  (uint8)
-//   phase 2 vertical taps from smem                      -> smem res[3][28][tile_w]        (uint8)
-//   phase 3 LUT + patch-order gather smem -> smem; a tile's tokens are one contiguous span of pixel_values, which
-//           leaves the SM as a single cp.async.bulk (TMA engine) copy per tile.
+// HBM-bound by design (3.84 MB read + 15.6 MB bf16 written per letter page). Each input byte crosses HBM once (plus the
+// filter halo between tiles), each output element is written once.
+//   tile  = (page, strip of 28 output rows = one merge row, chunk of tile_w output columns); CTAs walk tiles persistently
+//   load  the tile's input rows arrive in shared memory as whole 16-byte vectors (cp.async.cg, aligned 128-bit global
+//         reads; a row keeps its sub-vector misalignment, recorded per row) and the NEXT tile's rows are requested before
+//         this tile is computed: the global round trip hides behind a tile of arithmetic
+//   pass 1 horizontal taps: one thread per output column keeps its filter as packed int16 pairs in registers and runs
+//         down rows of equal alignment, two aligned words -> funnel shift -> dp2a (two taps per instruction); Pillow's
+//         22-bit coefficients are split into two int16 halves (exact: the sum is linear)       -> mid[plane][row][x] u8
+//   pass 2 vertical taps (only when the height changes): four columns per thread, row pairs interleaved with prmt so that
+//         dp2a again takes two taps at a time                                                  -> res[plane][28][x] u8
+//   pass 3 normalise (3x256 f32 LUT) + patch order: one thread per 28-pixel row of a merge cell, both temporal copies
+//         written from one read into a staged copy of the tile's tokens, which are ONE contiguous span of pixel_values:
+//         the tile leaves the SM as a single cp.async.bulk (TMA engine, no LSU store traffic)
+// Gray pages (do_convert_rgb) are filtered once and normalised three times; interleaved RGB is split into planes in
+// shared memory first.
 #include <map>
 #include <tuple>
 #include <vector>
@@ -21,27 +30,33 @@ namespace kocr {
 
 struct PageJob {
   const uint8_t* src;
-  const int32_t* hb;  // horizontal bounds [out_w][2], or null when the width does not change
-  const int32_t* hc;  // horizontal coeffs [out_w][hk]
-  const int32_t* vb;  // vertical bounds [out_h][2], or null
-  const int32_t* vc;  // vertical coeffs [out_h][vk]
+  const int32_t* hb;   // horizontal bounds [out_w][2] (first input column, taps), or null when the width does not change
+  const uint32_t* hp;  // horizontal taps as int16 pairs [out_w][hkp * hsets]
+  const int32_t* vb;   // vertical bounds [out_h][2], or null
+  const uint32_t* vp;  // vertical pairs [out_h][vkp * vsets]
   long long token_base;
-  long long src_bytes;    // size of the image buffer (staging never reads past it)
-  long long chan_stride;  // bytes between channels of one pixel (0 for gray: do_convert_rgb replicates)
+  long long src_bytes;    // size of the image buffer (loads never start past its 16-byte rounded end)
+  long long chan_stride;  // bytes between the planes of a planar image
   int row_pitch;          // bytes between rows
-  int pix_stride;         // bytes between horizontally adjacent pixels
+  int pix_stride;         // bytes between horizontally adjacent pixels (3 = interleaved RGB)
   int in_h, in_w, layout;
   int out_h, out_w;
-  int hk, hprec, vk, vprec;
+  int hkp, hsets, hprec, vkp, vsets, vprec;  // pairs per output, 1 set (int16 taps) or 2 (hi / lo halves of 22-bit taps)
   int tile_w, tiles_x, tile_base;
+};
+
+struct TileInfo {
+  int job, valid;
+  int y0, x0, tw, r0, rows_in, xin0, ncols_in;
+  int nseg, planes, Lp, nvec;   // staged segments (3 planar / 1), filtered planes (1 gray / 3), staged row pitch, vectors per row
+  long long n0;                 // first token of the tile
 };
 
 static constexpr int kStrip = 28;       // output rows per tile = patch * merge
 static constexpr int kPatchDim = 1176;  // 3 * 2 * 14 * 14
 static constexpr int kThreads = 256;
-static constexpr int kMaxStageRows = 768;  // staged input rows per tile (3 planes x up to 256 rows)
-static constexpr int kMaxDynSmem = 208 * 1024;  // dynamic shared memory opt-in; + ~10 KB static (LUT, job, row pointers) <= 227 KB
-static constexpr int kRB = 14;           // rows of horizontal-pass accumulators held in registers per thread
+static constexpr int kMaxPairs = 4;     // fast passes hold up to 8 taps per output; larger filters take the generic loops
+static constexpr int kMaxDynSmem = 200 * 1024;
 
 // 1-D bulk async copy shared -> global (TMA engine, no tensor map): size and both addresses multiples of 16 bytes
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -53,211 +68,299 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
 
-__device__ __forceinline__ uint8_t load_px(const PageJob& j, int c, int r, int x) {
-  return __ldg(j.src + c * j.chan_stride + (long long)r * j.row_pitch + x * j.pix_stride);
+// Which tile is it, and what does it read: evaluated by one thread, a tile ahead of its use.
+__device__ void plan_tile(const PageJob* __restrict__ jobs, int n_jobs, int tile, int n_tiles, TileInfo& t) {
+  t.valid = tile < n_tiles;
+  if (!t.valid) return;
+  int lo = 0, hi = n_jobs - 1;  // last job with tile_base <= tile
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_base <= tile) lo = mid; else hi = mid - 1;
+  }
+  const PageJob& j = jobs[lo];
+  t.job = lo;
+  const int local = tile - j.tile_base;
+  const int sy = local / j.tiles_x, tx = local % j.tiles_x;
+  t.y0 = sy * kStrip;
+  t.x0 = tx * j.tile_w;
+  t.tw = min(j.tile_w, j.out_w - t.x0);  // multiple of 28
+  t.r0 = t.y0;
+  t.rows_in = kStrip;
+  if (j.vb) {
+    t.r0 = j.vb[2 * t.y0];
+    t.rows_in = j.vb[2 * (t.y0 + kStrip - 1)] + j.vb[2 * (t.y0 + kStrip - 1) + 1] - t.r0;
+  }
+  t.xin0 = t.x0;
+  t.ncols_in = t.tw;
+  if (j.hb) {
+    t.xin0 = j.hb[2 * t.x0];
+    t.ncols_in = j.hb[2 * (t.x0 + t.tw - 1)] + j.hb[2 * (t.x0 + t.tw - 1) + 1] - t.xin0;
+  }
+  t.nseg = j.layout == KOCR_LAYOUT_CHW ? 3 : 1;
+  t.planes = j.layout == KOCR_LAYOUT_GRAY ? 1 : 3;
+  // a staged row = the 16-byte vectors that cover its bytes, plus 16 bytes of slack for the passes' whole-word reads
+  t.nvec = (15 + t.ncols_in * j.pix_stride + 15) >> 4;
+  t.Lp = (t.nvec + 1) * 16;
+  t.n0 = j.token_base + ((long long)sy * (j.out_w / kStrip) + t.x0 / kStrip) * 4;
+}
+
+// Request the tile's input rows: every thread issues whole 16-byte vectors; row i of segment s lands at stage + (s*rows_in+i)*Lp
+// starting `rowoff` bytes in (the row's misalignment against 16 bytes in global memory).
+__device__ __forceinline__ void request_rows(const PageJob& j, const TileInfo& t, uint8_t* stage, uint8_t* rowoff) {
+  const int nrows = t.nseg * t.rows_in;
+  const uintptr_t img_end = (reinterpret_cast<uintptr_t>(j.src) + (uintptr_t)j.src_bytes + 15) & ~uintptr_t(15);
+  const uint32_t stage_u32 = smem_u32(stage);
+  const int total = nrows * t.nvec;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const int row = i / t.nvec, v = i - row * t.nvec;
+    const int sg = row / t.rows_in, r = row - sg * t.rows_in;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(j.src) + (uintptr_t)(sg * j.chan_stride) + (uintptr_t)((long long)(t.r0 + r) * j.row_pitch) +
+                        (uintptr_t)((long long)t.xin0 * j.pix_stride);
+    const uintptr_t a = (p & ~uintptr_t(15)) + 16u * (uintptr_t)v;
+    if (v == 0) rowoff[row] = (uint8_t)(p & 15);
+    if (a < img_end) cp_async16(stage_u32 + (uint32_t)(row * t.Lp + v * 16), reinterpret_cast<const void*>(a));
+  }
 }
 
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* __restrict__ jobs, int n_jobs,
                                                               int n_tiles, const float* __restrict__ lut_g,
-                                                              void* __restrict__ out, int max_mid_bytes, int coef_off, int out_off) {
+                                                              void* __restrict__ out, int stage_bytes, int planar_off, int tab_off,
+                                                              int mid_off, int res_off, int out_off) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float lut[768];
-  __shared__ PageJob job;
-  __shared__ uintptr_t row_ptr[kMaxStageRows];
+  __shared__ TileInfo tinfo[2];
+  __shared__ uint8_t rowoff[2][3 * 256];
   for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();  // previous tile's smem and `job` fully consumed
-    if (threadIdx.x == 0) {
-      int lo = 0, hi = n_jobs - 1;  // last job with tile_base <= tile
-      while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile_base <= tile) lo = mid; else hi = mid - 1;
-      }
-      job = jobs[lo];
-    }
-    __syncthreads();
-    const PageJob& j = job;
-    const int local = tile - j.tile_base;
-    const int sy = local / j.tiles_x, tx = local % j.tiles_x;
-    const int y0 = sy * kStrip;
-    const int x0 = tx * j.tile_w;
-    const int tw = min(j.tile_w, j.out_w - x0);  // multiple of 28
-    int r0 = y0, rows_in = kStrip;
-    if (j.vb) {
-      r0 = j.vb[2 * y0];
-      rows_in = j.vb[2 * (y0 + kStrip - 1)] + j.vb[2 * (y0 + kStrip - 1) + 1] - r0;
-    }
-    uint8_t* mid = smem;                                   // [3][rows_in][tw]
-    uint8_t* res = j.vb ? smem + max_mid_bytes : smem;     // [3][28][tw]
+  int buf = 0;
+  if (threadIdx.x == 0) plan_tile(jobs, n_jobs, blockIdx.x, n_tiles, tinfo[0]);
+  __syncthreads();
+  if (tinfo[0].valid) request_rows(jobs[tinfo[0].job], tinfo[0], smem, rowoff[0]);
+  cp_async_commit();
 
-    // ---- phase 0: stage the input rows of this tile in smem with aligned 32-bit loads, all in flight at once (one
-    // global-latency round trip per tile instead of one per filter tap). Rows are re-aligned on the way (funnel shift of
-    // two aligned words): row r of segment s starts exactly at stage + (s*rows_in + r)*Lp.
-    int xin0 = x0, ncols_in = tw;
-    if (j.hb) {
-      xin0 = j.hb[2 * x0];
-      ncols_in = j.hb[2 * (x0 + tw - 1)] + j.hb[2 * (x0 + tw - 1) + 1] - xin0;
-    }
-    const int nseg = j.layout == KOCR_LAYOUT_CHW ? 3 : 1;     // planar: one segment per channel; interleaved / gray: one
-    const int Lp = ((ncols_in * j.pix_stride + 6) & ~3) + 4;  // staged bytes per row, a multiple of 4
-    const int wpr = Lp >> 2;
-    uint8_t* stage = smem + out_off;  // aliases the output staging buffer (free until phase 3)
-    const uint8_t* seg0 = j.src + (long long)r0 * j.row_pitch + (long long)xin0 * j.pix_stride;
-    if (threadIdx.x == 0) bulk_store_wait_read();  // the previous tile's bulk copy has finished reading that buffer
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    // ---- a tile ahead: plan the next tile and request its rows into the other stage buffer (its previous reader, pass 1
+    // of the tile before this one, is two barriers behind)
+    if (threadIdx.x == 0) plan_tile(jobs, n_jobs, tile + gridDim.x, n_tiles, tinfo[buf ^ 1]);
     __syncthreads();
-    {
-      const uintptr_t img_end = (reinterpret_cast<uintptr_t>(j.src) + j.src_bytes + 3) & ~uintptr_t(3);
-      uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
-      const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-      const int nrows = nseg * rows_in;
-      constexpr int kWarps = kThreads / 32, kRowsInFlight = 6;
-      // the 64-bit address of every staged row is worked out once per tile (one thread per row), not per lane and word
-      for (int sr = threadIdx.x; sr < nrows; sr += kThreads) {
-        const int sg = sr >= 2 * rows_in ? 2 : (sr >= rows_in ? 1 : 0);
-        row_ptr[sr] = reinterpret_cast<uintptr_t>(seg0 + sg * j.chan_stride + (long long)(sr - sg * rows_in) * j.row_pitch);
+    const TileInfo& t = tinfo[buf];
+    const PageJob& j = jobs[t.job];
+    if (tinfo[buf ^ 1].valid)
+      request_rows(jobs[tinfo[buf ^ 1].job], tinfo[buf ^ 1], smem + (buf ^ 1) * stage_bytes, rowoff[buf ^ 1]);
+    cp_async_commit();
+
+    const int tw = t.tw, rows_in = t.rows_in, planes = t.planes;
+    uint8_t* stage = smem + buf * stage_bytes;
+    uint8_t* mid = smem + mid_off;                            // [planes][rows_in + 1][tw]
+    uint8_t* res = j.vb ? smem + res_off : mid;               // [planes][28][tw]
+    const int mid_plane = (rows_in + 1) * tw;
+    const int hpw = j.hkp * j.hsets;                          // u32 per output column in the tap table
+    // ---- this tile's horizontal taps: (first input column relative to the tile, pairs) per output column, to shared memory
+    int32_t* xoff = reinterpret_cast<int32_t*>(smem + tab_off);            // [tw]
+    uint32_t* htab = reinterpret_cast<uint32_t*>(smem + tab_off) + 112;    // [tw][hpw]
+    if (j.hb) {
+      for (int x = threadIdx.x; x < tw; x += kThreads) xoff[x] = j.hb[2 * (t.x0 + x)] - t.xin0;
+      for (int i = threadIdx.x; i < tw * hpw; i += kThreads) htab[i] = j.hp[(size_t)t.x0 * hpw + i];
+    }
+    cp_async_wait<1>();  // this tile's rows have landed (the next tile's may still be in flight)
+    __syncthreads();
+
+    // ---- interleaved RGB: split the staged rows into planes (aligned rows, pitch Lq) so that pass 1 sees adjacent taps
+    const uint8_t* rows_base = stage;
+    int row_pitch_s = t.Lp, seg_rows = rows_in;
+    bool aligned_rows = false;
+    if (j.layout == KOCR_LAYOUT_HWC) {
+      uint8_t* planar = smem + planar_off;
+      const int Lq = (t.ncols_in + 12 + 3) & ~3;
+      for (int i = threadIdx.x; i < rows_in * t.ncols_in; i += kThreads) {
+        const int r = i / t.ncols_in, x = i - r * t.ncols_in;
+        const uint8_t* p = stage + r * t.Lp + rowoff[buf][r] + 3 * x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) planar[(c * rows_in + r) * Lq + x] = p[c];
       }
       __syncthreads();
-      // warp per staged row, lanes over its words; kRowsInFlight rows are requested before the first is consumed, and
-      // the upper word of each funnel shift comes from the neighbouring lane instead of a second load
-      for (int wd0 = 0; wd0 < wpr; wd0 += 32) {
-        const int wd = wd0 + lane;
-        for (int sr0 = wrp; sr0 < nrows; sr0 += kWarps * kRowsInFlight) {
-          uint32_t lo[kRowsInFlight], nx[kRowsInFlight];
-          int sh[kRowsInFlight];
+      rows_base = planar;
+      row_pitch_s = Lq;
+      aligned_rows = true;
+    }
+
+    // ---- pass 1: horizontal. Thread = (output column x, alignment class rho): the rows r = rho, rho+4, ... of a segment
+    // share their misalignment modulo 4 when walked with a constant pitch, so the word offset and the funnel-shift amount of
+    // the column's tap window are loop constants; per row: three aligned words, two funnel shifts, one dp2a per tap pair.
+    if (j.hb && j.hkp <= kMaxPairs) {
+      const int lanes_x = tw;                           // threads with the same rho
+      const int nrho = min(4, kThreads / lanes_x);      // classes handled at once (2 for a 112-column tile)
+      const int x = threadIdx.x % lanes_x, grp = threadIdx.x / lanes_x;
+      if (grp < nrho) {
+        const int xo = xoff[x];
+        uint32_t kp[2][kMaxPairs];
 #pragma unroll
-          for (int b = 0; b < kRowsInFlight; ++b) {
-            const int sr = sr0 + b * kWarps;
-            lo[b] = nx[b] = 0u;
-            sh[b] = 0;
-            if (sr < nrows) {
-              const uintptr_t p = row_ptr[sr];
-              const uintptr_t a = (p & ~uintptr_t(3)) + 4u * wd;
-              sh[b] = (int)(p & 3) * 8;
-              if (wd <= wpr && a < img_end) lo[b] = __ldg(reinterpret_cast<const uint32_t*>(a));
-              if (lane == 31 && sh[b] != 0 && a + 4 < img_end) nx[b] = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+          for (int k = 0; k < kMaxPairs; ++k) kp[s2][k] = (s2 < j.hsets && k < j.hkp) ? htab[x * hpw + s2 * j.hkp + k] : 0u;
+        const int round0 = 1 << (j.hprec - 1);
+        const bool split = j.hsets == 2;
+        for (int rho = grp; rho < 4; rho += nrho) {
+          for (int pl = 0; pl < planes; ++pl) {
+            const int sg = t.nseg == 3 ? pl : 0;
+            const uint8_t* segp = rows_base + (size_t)(aligned_rows ? pl : sg) * seg_rows * row_pitch_s;
+            for (int r = rho; r < rows_in; r += 4) {
+              const int boff = (aligned_rows ? 0 : rowoff[buf][sg * rows_in + r]) + xo;   // byte offset of the first tap in the staged row
+              const uint32_t a = smem_u32(segp + (size_t)r * row_pitch_s) + (uint32_t)(boff & ~3);
+              const int sh = (boff & 3) * 8;
+              const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+              const uint32_t p = __funnelshift_r(w0, w1, sh), q = __funnelshift_r(w1, w2, sh);  // taps 0..3, 4..7
+              int acc = __dp2a_lo((int)kp[0][0], p, 0);
+              acc = __dp2a_hi((int)kp[0][1], p, acc);
+              acc = __dp2a_lo((int)kp[0][2], q, acc);
+              acc = __dp2a_hi((int)kp[0][3], q, acc);
+              if (split) {  // 22-bit taps = hi * 2^11 + lo, both halves int16: sum = (sum_hi << 11) + sum_lo, exactly
+                int lo = __dp2a_lo((int)kp[1][0], p, 0);
+                lo = __dp2a_hi((int)kp[1][1], p, lo);
+                lo = __dp2a_lo((int)kp[1][2], q, lo);
+                lo = __dp2a_hi((int)kp[1][3], q, lo);
+                acc = (acc << 11) + lo;
+              }
+              mid[pl * mid_plane + r * tw + x] = (uint8_t)sat_u8((acc + round0) >> j.hprec);
             }
-          }
-#pragma unroll
-          for (int b = 0; b < kRowsInFlight; ++b) {
-            const int sr = sr0 + b * kWarps;
-            const uint32_t up = __shfl_down_sync(0xffffffffu, lo[b], 1);
-            const uint32_t hi = lane == 31 ? nx[b] : up;
-            if (sr < nrows && wd < wpr) sw[sr * wpr + wd] = __funnelshift_r(lo[b], hi, sh[b]);  // byte k = byte k of the image row
           }
         }
       }
-    }
-    if (j.hb) {
-      int32_t* kcoef = reinterpret_cast<int32_t*>(smem + coef_off);  // [hk][tw] transposed: conflict-free
-      for (int i = threadIdx.x; i < j.hk * tw; i += kThreads) {
-        const int t = i / tw, x = i % tw;
-        kcoef[i] = j.hc[(size_t)(x0 + x) * j.hk + t];
-      }
-    }
-    __syncthreads();
-
-    // ---- phase 1: horizontal pass (or plain copy) stage -> mid. One thread per output column: its tap window and
-    // coefficients are read once and reused for every row and channel (kRB rows of accumulators in registers).
-    {
-      const int groups = kThreads / tw;  // thread = (output column, row-block group): keeps all lanes busy at any tile width
-      const int x = threadIdx.x % tw, grp = threadIdx.x / tw;
-      const int chan_in_row = j.layout == KOCR_LAYOUT_HWC ? 1 : 0;  // byte step between channels inside a staged row
-      const uint32_t stage_u32 = smem_u32(stage);
-      if (grp < groups) {
-        int xmin = x0 + x, cnt = 1;
-        if (j.hb) { xmin = j.hb[2 * (x0 + x)]; cnt = j.hb[2 * (x0 + x) + 1]; }
-        const int32_t* kcoef = reinterpret_cast<const int32_t*>(smem + coef_off);
-        const int round0 = j.hb ? 1 << (j.hprec - 1) : 0;
-        const int shr = j.hb ? j.hprec : 0;
-        const int col_off = (xmin - xin0) * j.pix_stride;
-        for (int rb = grp * kRB; rb < rows_in; rb += kRB * groups) {
-          int acc[3][kRB];
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < kRB; ++r) acc[c][r] = round0;
-          const int nr = min(kRB, rows_in - rb);
-          // rows past the strip's last input row read padding of the staging buffer; their sums are discarded below
-          for (int t = 0; t < cnt; ++t) {
-            const int kt = j.hb ? kcoef[t * tw + x] : 1;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const int sg = nseg == 3 ? c : 0;
-              uint32_t a = stage_u32 + (uint32_t)((sg * rows_in + rb) * Lp + col_off + t * j.pix_stride + c * chan_in_row);
-#pragma unroll
-              for (int r = 0; r < kRB; ++r, a += Lp) acc[c][r] += (int)lds_u8(a) * kt;
+    } else {
+      // generic: any filter length (strong downscales), or no horizontal resize at all (copy)
+      for (int i = threadIdx.x; i < planes * rows_in * tw; i += kThreads) {
+        const int x = i % tw, rr = i / tw;
+        const int pl = rr / rows_in, r = rr - pl * rows_in;
+        const int sg = t.nseg == 3 ? pl : 0;
+        const uint8_t* rowp = aligned_rows ? rows_base + (size_t)(pl * seg_rows + r) * row_pitch_s
+                                           : rows_base + (size_t)(sg * rows_in + r) * row_pitch_s + rowoff[buf][sg * rows_in + r];
+        int v;
+        if (j.hb) {
+          const int xmin = j.hb[2 * (t.x0 + x)] - t.xin0, cnt = j.hb[2 * (t.x0 + x) + 1];
+          const uint32_t* kk = j.hp + (size_t)(t.x0 + x) * hpw;
+          int hi = 0, lo = 0;
+          for (int k = 0; k < cnt; ++k) {
+            const int px = rowp[xmin + k];
+            const uint32_t w = kk[k >> 1];
+            hi += px * (int)(int16_t)((k & 1) ? (w >> 16) : (w & 0xffff));
+            if (j.hsets == 2) {
+              const uint32_t w2 = kk[j.hkp + (k >> 1)];
+              lo += px * (int)(int16_t)((k & 1) ? (w2 >> 16) : (w2 & 0xffff));
             }
           }
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < kRB; ++r)
-              if (r < nr) mid[((size_t)c * rows_in + rb + r) * tw + x] = (uint8_t)min(max(acc[c][r] >> shr, 0), 255);
+          const int acc = j.hsets == 2 ? (hi << 11) + lo : hi;
+          v = sat_u8((acc + (1 << (j.hprec - 1))) >> j.hprec);
+        } else {
+          v = rowp[x];
         }
+        mid[pl * mid_plane + r * tw + x] = (uint8_t)v;
       }
     }
     __syncthreads();
 
-    // ---- phase 2: vertical pass mid -> res
+    // ---- pass 2: vertical mid -> res. Thread = (4 columns, plane, third of the strip): rows t and t+1 of the four columns are
+    // interleaved by prmt into (t, t+1) byte pairs, so one dp2a applies a pair of taps to one column.
     if (j.vb) {
-      const int n2 = 3 * kStrip * tw;
-      for (int i = threadIdx.x; i < n2; i += kThreads) {
-        const int x = i % tw;
-        const int yc = i / tw;
-        const int y = yc % kStrip, c = yc / kStrip;
-        const int ymin = j.vb[2 * (y0 + y)] - r0, cnt = j.vb[2 * (y0 + y) + 1];
-        const int32_t* k = j.vc + (size_t)(y0 + y) * j.vk;
-        const uint8_t* col = mid + ((size_t)c * rows_in + ymin) * tw + x;
-        int acc = 1 << (j.vprec - 1);
-        for (int t = 0; t < cnt; ++t) acc += (int)col[(size_t)t * tw] * k[t];
-        res[i] = (uint8_t)min(max(acc >> j.vprec, 0), 255);
+      const int groups = tw >> 2;
+      const int vpw = j.vkp * j.vsets;
+      const int items = planes * groups;
+      const int ysplit = max(1, min(kStrip, kThreads / items));        // concurrent slices of the 28 output rows
+      const int it = threadIdx.x % items, ys = threadIdx.x / items;
+      if (ys < ysplit) {
+        const int pl = it / groups, xg = it - pl * groups;
+        const int round0 = 1 << (j.vprec - 1);
+        for (int y = ys; y < kStrip; y += ysplit) {
+          const int ymin = j.vb[2 * (t.y0 + y)] - t.r0, cnt = j.vb[2 * (t.y0 + y) + 1];
+          const uint32_t* kk = j.vp + (size_t)(t.y0 + y) * vpw;
+          const uint32_t a0 = smem_u32(mid + pl * mid_plane + ymin * tw + 4 * xg);
+          int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+          for (int k = 0; 2 * k < cnt; ++k) {
+            const uint32_t wa = lds_u32(a0 + (uint32_t)(2 * k * tw)), wb = lds_u32(a0 + (uint32_t)((2 * k + 1) * tw));  // row ymin+cnt may be one past: its tap is 0
+            const uint32_t ab = __byte_perm(wa, wb, 0x5140), cd = __byte_perm(wa, wb, 0x7362);   // (a0 b0 a1 b1), (a2 b2 a3 b3)
+            const int k0 = (int)__ldg(kk + k);
+            hi[0] = __dp2a_lo(k0, ab, hi[0]);
+            hi[1] = __dp2a_hi(k0, ab, hi[1]);
+            hi[2] = __dp2a_lo(k0, cd, hi[2]);
+            hi[3] = __dp2a_hi(k0, cd, hi[3]);
+            if (j.vsets == 2) {
+              const int k1 = (int)__ldg(kk + j.vkp + k);
+              lo[0] = __dp2a_lo(k1, ab, lo[0]);
+              lo[1] = __dp2a_hi(k1, ab, lo[1]);
+              lo[2] = __dp2a_lo(k1, cd, lo[2]);
+              lo[3] = __dp2a_hi(k1, cd, lo[3]);
+            }
+          }
+          uint32_t packed = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int acc = j.vsets == 2 ? (hi[e] << 11) + lo[e] : hi[e];
+            packed |= (uint32_t)sat_u8((acc + round0) >> j.vprec) << (8 * e);
+          }
+          *reinterpret_cast<uint32_t*>(res + (pl * kStrip + y) * tw + 4 * xg) = packed;
+        }
       }
       __syncthreads();
     }
 
-    // ---- phase 3: normalise + patch order, staged in smem. One thread per (token, channel, patch row) run of 14 px:
-    // 7 two-byte loads, 14 LUT reads, the run written for both temporal copies. The tile's tokens are ONE contiguous
-    // span of pixel_values, so the whole staged tile leaves with a single bulk async copy (no LSU store traffic).
+    // ---- pass 3: normalise + patch order, staged in smem. Thread = (merge cell, row of the strip, channel): 28 pixels = seven
+    // aligned words, 28 LUT reads, and the two 14-pixel runs (mw = 0 / 1) written for both temporal copies. The tile's tokens
+    // are ONE contiguous span of pixel_values, so the whole staged tile leaves with a single bulk async copy.
     const int cells = tw / kStrip;
-    const int gw2 = j.out_w / kStrip;  // merge cells per row
-    const long long n0 = j.token_base + ((long long)sy * gw2 + x0 / kStrip) * 4;
     constexpr int kElt = kBf16 ? 2 : 4;
-    uint8_t* obuf = smem + out_off;  // the staged input it aliased was consumed in phase 1 (two barriers ago)
-    const int runs = cells * 4 * 42;
-    for (int run = threadIdx.x; run < runs; run += kThreads) {
-      const int t = run / 42, rr = run % 42;
-      const int c = rr / 14, py = rr % 14;
-      const int cell = t >> 2, mh = (t >> 1) & 1, mw = t & 1;
-      const uint16_t* p = reinterpret_cast<const uint16_t*>(res + ((size_t)c * kStrip + mh * 14 + py) * tw + cell * kStrip + mw * 14);
-      uint8_t* d = obuf + ((size_t)t * kPatchDim + c * 392 + py * 14) * kElt;
+    uint8_t* obuf = smem + out_off;
+    if (threadIdx.x == 0) bulk_store_wait_read();  // the previous tile's bulk copy has finished reading obuf
+    __syncthreads();
+    const int res_plane = (j.vb ? kStrip : rows_in + 1) * tw;
+    for (int item = threadIdx.x; item < cells * kStrip * 3; item += kThreads) {
+      const int c = item / (cells * kStrip), rem = item - c * (cells * kStrip);
+      const int cell = rem / kStrip, y = rem - cell * kStrip;
+      const int mh = y >= 14 ? 1 : 0, py = y - 14 * mh;
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(res + (planes == 1 ? 0 : c) * res_plane + y * tw + cell * kStrip);
       const float* l = lut + c * 256;
+      uint8_t* d0 = obuf + ((size_t)(cell * 4 + mh * 2) * kPatchDim + c * 392 + py * 14) * kElt;  // token mw = 0; mw = 1 is kPatchDim further
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         const uint32_t u = p[k];
-        const float v0 = l[u & 255], v1 = l[u >> 8];
+        const float v0 = l[u & 255], v1 = l[(u >> 8) & 255], v2 = l[(u >> 16) & 255], v3 = l[u >> 24];
+        // pixels 4k..4k+3 of the 28: pixel pairs never straddle the two tokens (14 is even)
+        const int pa = 4 * k, pb = 4 * k + 2;
+        uint8_t* da = d0 + ((pa >= 14 ? kPatchDim - 14 : 0) + pa) * kElt;
+        uint8_t* db = d0 + ((pb >= 14 ? kPatchDim - 14 : 0) + pb) * kElt;
         if (kBf16) {
-          const uint32_t pk = pack_bf16(v0, v1);
-          reinterpret_cast<uint32_t*>(d)[k] = pk;
-          reinterpret_cast<uint32_t*>(d + 196 * kElt)[k] = pk;  // tp = 1 copy
+          const uint32_t ka = pack_bf16(v0, v1), kb = pack_bf16(v2, v3);
+          *reinterpret_cast<uint32_t*>(da) = ka;
+          *reinterpret_cast<uint32_t*>(da + 196 * kElt) = ka;  // tp = 1 copy
+          *reinterpret_cast<uint32_t*>(db) = kb;
+          *reinterpret_cast<uint32_t*>(db + 196 * kElt) = kb;
         } else {
-          reinterpret_cast<float2*>(d)[k] = make_float2(v0, v1);
-          reinterpret_cast<float2*>(d + 196 * kElt)[k] = make_float2(v0, v1);
+          *reinterpret_cast<float2*>(da) = make_float2(v0, v1);
+          *reinterpret_cast<float2*>(da + 196 * kElt) = make_float2(v0, v1);
+          *reinterpret_cast<float2*>(db) = make_float2(v2, v3);
+          *reinterpret_cast<float2*>(db + 196 * kElt) = make_float2(v2, v3);
         }
       }
     }
     fence_proxy_async();  // make the generic-proxy smem writes visible to the bulk copy engine
     __syncthreads();
     if (threadIdx.x == 0)
-      bulk_store(reinterpret_cast<uint8_t*>(out) + n0 * kPatchDim * kElt, obuf, (uint32_t)(cells * 4 * kPatchDim * kElt));
+      bulk_store(reinterpret_cast<uint8_t*>(out) + t.n0 * kPatchDim * kElt, obuf, (uint32_t)(cells * 4 * kPatchDim * kElt));
   }
+  cp_async_wait<0>();
   if (threadIdx.x == 0) bulk_store_wait_all();
 }
 
