@@ -310,6 +310,22 @@ def run_gpu(args):
     ms_e2e = timed(e2e_steps_all, args.steps, after=drain_e2e)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- extras on every rank (they shard work): the C5 bulk job (strong scaling) and the same pipeline fed
+    # with undecoded PNG files (row f2: decode on the GPU inside the timed region)
+    extras = {}
+    if args.workload == "c2" and not args.no_c5:
+        job_pages = args.job_pages if world > 1 else min(args.job_pages, 1024)
+        ms_j, _, n_mine, _ = bulk_job(enc, vars(cfg), world, rank, dev, job_pages, 1, 1)
+        extras["c5_bulk_job"] = {"value": job_pages / (ms_j / 1e3), "unit": UNIT, "scaling": "strong", "job_pages": job_pages,
+                                 "seconds": ms_j / 1e3, "pages_per_rank": n_mine,
+                                 "what": "one job of job_pages letter pages sharded over the ranks (LPT, no collective), 64-page batches, "
+                                         "pinned host pages in -> host embeddings out; 8192 pages at N > 1, 1024 at N = 1"}
+        png_pages = 256 * world
+        ms_p, _, _, h2d_p = bulk_job(enc, vars(cfg), world, rank, dev, png_pages, 1, 1, png=True)
+        extras["e2e_from_png"] = {"value": png_pages / (ms_p / 1e3), "unit": UNIT, "job_pages": png_pages, "h2d_bytes_per_rank": h2d_p,
+                                  "what": "same job with the pages given as RGB PNG files: inflate + scan-line filters on the GPU inside the "
+                                          "timed region, only compressed bytes cross PCIe"}
+
     if rank == 0:
         pk = peaks()
         value = world * n_pages * args.steps / (ms / 1e3)
@@ -366,41 +382,44 @@ def run_gpu(args):
             run_once()                       # warm-up page (thread pools, oneDNN primitive caches)
             spp = run_once()                 # one full-depth page: the bounded CPU sample (~10-30 s)
             line["cpu_baseline"] = {"value": 1.0 / spp, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": desc}
+        if extras:
+            line.setdefault("extra", {}).update(extras)
         if world == 1 and args.library_baselines and args.workload == "c2":
             del d_pages, h_pages
             torch.cuda.empty_cache()
-            line["extra"] = {"library_baselines_same_gpu": library_baselines(),
-                             "note": "tower only, 16 C2 pages per call, bf16, random weights; 'this repo' line in the same list for the like-for-like"}
+            line.setdefault("extra", {}).update({
+                "library_baselines_same_gpu": library_baselines(),
+                "library_baselines_note": "tower only, 16 C2 pages per call, bf16, random weights; 'this repo' line in the same list for the like-for-like"})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------- C5: bulk job, strong scaling
-def run_bulk_job(args):
-    """one job of `--job-pages` letter pages (C2's generator), page-sharded over the ranks with
-    shard_pages (no collective), each rank streaming its shard through PageEncoder.encode_to_host_async in 64-page
-    batches: pinned host pages in, embeddings in pinned host memory out. A step is the whole job; scaling is strong."""
+def bulk_job(enc, cfg, world, rank, dev, total, steps=1, warmup=1, png=False):
+    """One job of `total` letter pages (C2's generator), page-sharded over the ranks with shard_pages (no collective), each
+    rank streaming its shard through PageEncoder.encode_to_host_async in 64-page batches: pinned host pages in (or, with
+    png=True, the pages' PNG files, decoded on the GPU - SURVEY.md section 8 row f2), embeddings in pinned host memory out.
+    Returns (ms for `steps` jobs as the max over ranks, launches, pages of this rank, h2d bytes per job of this rank)."""
     import torch.distributed as dist
 
-    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, page_cost, presets, shard_pages
+    from karanta_ocr_b200 import page_cost, shard_pages
+    if png:
+        import io
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a GPU: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = presets.preset("qwen2_vl_7b")
-    tower = KarantaVisionTower(cfg, device=dev)
-    tower.load_state_dict(presets.random_state_dict(cfg, seed=0))
-    enc = PageEncoder(tower, MIN_PIXELS, MAX_PIXELS)
-    pool = [torch.from_numpy(p).pin_memory() for p in make_pages(PAGES_PER_STEP)]  # the job cycles over 64 distinct pinned pages
-    total = args.job_pages
-    cost = page_cost(pool[0].shape[1], pool[0].shape[2], MIN_PIXELS, MAX_PIXELS)
+        from PIL import Image
+        pool = []
+        for p in make_pages(8):  # what pdftoppm -png hands over: 8-bit RGB PNG files
+            buf = io.BytesIO()
+            Image.fromarray(np.ascontiguousarray(p.transpose(1, 2, 0))).save(buf, format="PNG")
+            pool.append(buf.getvalue())
+        h, w = PAGE_H, PAGE_W
+        nbytes = [len(b) for b in pool]
+    else:
+        pool = [torch.from_numpy(p).pin_memory() for p in make_pages(PAGES_PER_STEP)]  # the job cycles over 64 distinct pinned pages
+        h, w = pool[0].shape[1], pool[0].shape[2]
+        nbytes = [int(t.numel()) for t in pool]
+    cost = page_cost(h, w, MIN_PIXELS, MAX_PIXELS)
     mine = shard_pages([cost] * total, world)[rank]
     rows = (92 * 72) // 4
     outs = [torch.empty((PAGES_PER_STEP * rows, cfg["out_hidden"]), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
@@ -424,16 +443,13 @@ def run_bulk_job(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         job(mine[:PAGES_PER_STEP])  # warm-up = one batch per rank, not a whole job
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     launches = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         launches += job(mine)
     e1.record()
     torch.cuda.synchronize()
@@ -441,17 +457,45 @@ def run_bulk_job(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     barrier()
+    return float(ms.item()), launches, len(mine), int(sum(nbytes[i % len(pool)] for i in mine))
+
+
+def run_bulk_job(args):
+    """one job of `--job-pages` letter pages, strong scaling. A step is the whole job."""
+    import torch.distributed as dist
+
+    from karanta_ocr_b200 import KarantaVisionTower, PageEncoder, presets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = presets.preset("qwen2_vl_7b")
+    tower = KarantaVisionTower(cfg, device=dev)
+    tower.load_state_dict(presets.random_state_dict(cfg, seed=0))
+    enc = PageEncoder(tower, MIN_PIXELS, MAX_PIXELS)
+    total = args.job_pages
+    rows = (92 * 72) // 4
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, n_mine, h2d = bulk_job(enc, cfg, world, rank, dev, total, args.steps, args.warmup, png=args.png)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        value = total * args.steps / (float(ms.item()) / 1e3)
+        value = total * args.steps / (ms / 1e3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOADS["c5"], "job_pages": total, "pages_per_rank": len(mine), "batch_pages": PAGES_PER_STEP,
+                "config": {"workload": WORKLOADS["c5"], "job_pages": total, "pages_per_rank": n_mine, "batch_pages": PAGES_PER_STEP,
                            "parallelism": f"page-sharded x{world} (LPT), no collective, host-side results",
-                           "pages": "cycled from a pool of 64 distinct pinned host pages", "weights": "seeded random init"},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(sum(pool[i % len(pool)].numel() for i in mine)),
-                        "d2h_bytes_per_step": int(len(mine) * rows * cfg["out_hidden"] * 2)},
+                           "pages": ("8 distinct RGB PNG files cycled, decoded on the GPU (inflate + scan-line filters)" if args.png
+                                     else "cycled from a pool of 64 distinct pinned host pages"), "weights": "seeded random init"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_mine * rows * cfg["out_hidden"] * 2)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "note": "value is measured end to end (host pages in, host embeddings out); there is no device-resident variant of a bulk job"}
         print(json.dumps(line), flush=True)
@@ -472,7 +516,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = the metric's configuration (default); c3 / c4 = the other BASELINE.json configs, for the record; "
                          "c5 = one bulk job of --job-pages pages sharded over the ranks (strong scaling)")
-    ap.add_argument("--job-pages", type=int, default=8192, help="c5 only: pages in the whole job")
+    ap.add_argument("--job-pages", type=int, default=8192, help="pages in the C5 bulk job (--workload c5, and the c5_bulk_job extra of the default run)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 bulk-job and PNG-input extras of the default run")
+    ap.add_argument("--png", action="store_true", help="--workload c5: feed the job with PNG files decoded on the GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

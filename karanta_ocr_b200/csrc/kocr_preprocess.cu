@@ -20,6 +20,8 @@
 //         the tile leaves the SM as a single cp.async.bulk (TMA engine, no LSU store traffic)
 // Gray pages (do_convert_rgb) are filtered once and normalised three times; interleaved RGB is split into planes in
 // shared memory first.
+#include <stdlib.h>
+
 #include <map>
 #include <tuple>
 #include <vector>
@@ -81,16 +83,28 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   return v;
 }
 __device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
+// two taps per instruction: d = c + s16(a.lo) * u8(b.byte[0|2]) + s16(a.hi) * u8(b.byte[1|3])  (lo: bytes 0,1; hi: bytes 2,3)
+__device__ __forceinline__ int dp2a_lo_su(uint32_t taps, uint32_t px, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(px), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t taps, uint32_t px, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(px), "r"(c));
+  return d;
+}
 
-// Which tile is it, and what does it read: evaluated by one thread, a tile ahead of its use.
-__device__ void plan_tile(const PageJob* __restrict__ jobs, int n_jobs, int tile, int n_tiles, TileInfo& t) {
+// Which tile is it, and what does it read: evaluated by one thread, a tile ahead of its use. A CTA visits its tiles in
+// increasing order, so the job is found by walking on from the previous one (`cur`, `next_base` live in that thread's registers).
+__device__ void plan_tile(const PageJob* __restrict__ jobs, int n_jobs, int tile, int n_tiles, TileInfo& t, int& cur, int& next_base) {
   t.valid = tile < n_tiles;
   if (!t.valid) return;
-  int lo = 0, hi = n_jobs - 1;  // last job with tile_base <= tile
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].tile_base <= tile) lo = mid; else hi = mid - 1;
+  while (tile >= next_base) {
+    ++cur;
+    next_base = cur + 1 < n_jobs ? jobs[cur + 1].tile_base : 0x7fffffff;
   }
+  const int lo = cur;
   const PageJob& j = jobs[lo];
   t.job = lo;
   const int local = tile - j.tile_base;
@@ -148,22 +162,21 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
   for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
 
   int buf = 0;
-  if (threadIdx.x == 0) plan_tile(jobs, n_jobs, blockIdx.x, n_tiles, tinfo[0]);
+  int cur = 0, next_base = 0;  // thread 0: job of the last planned tile, first tile of the job after it
+  if (threadIdx.x == 0) {
+    next_base = n_jobs > 1 ? jobs[1].tile_base : 0x7fffffff;
+    plan_tile(jobs, n_jobs, blockIdx.x, n_tiles, tinfo[0], cur, next_base);
+  }
   __syncthreads();
   if (tinfo[0].valid) request_rows(jobs[tinfo[0].job], tinfo[0], smem, rowoff[0]);
   cp_async_commit();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    // ---- a tile ahead: plan the next tile and request its rows into the other stage buffer (its previous reader, pass 1
-    // of the tile before this one, is two barriers behind)
-    if (threadIdx.x == 0) plan_tile(jobs, n_jobs, tile + gridDim.x, n_tiles, tinfo[buf ^ 1]);
-    __syncthreads();
+    // ---- a tile ahead: thread 0 plans the next tile (a few dependent global reads) while the others fetch this tile's tap tables
+    // and wait for its rows; everybody meets at the barrier before pass 1
+    if (threadIdx.x == 0) plan_tile(jobs, n_jobs, tile + gridDim.x, n_tiles, tinfo[buf ^ 1], cur, next_base);
     const TileInfo& t = tinfo[buf];
     const PageJob& j = jobs[t.job];
-    if (tinfo[buf ^ 1].valid)
-      request_rows(jobs[tinfo[buf ^ 1].job], tinfo[buf ^ 1], smem + (buf ^ 1) * stage_bytes, rowoff[buf ^ 1]);
-    cp_async_commit();
-
     const int tw = t.tw, rows_in = t.rows_in, planes = t.planes;
     uint8_t* stage = smem + buf * stage_bytes;
     uint8_t* mid = smem + mid_off;                            // [planes][rows_in + 1][tw]
@@ -177,8 +190,13 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
       for (int x = threadIdx.x; x < tw; x += kThreads) xoff[x] = j.hb[2 * (t.x0 + x)] - t.xin0;
       for (int i = threadIdx.x; i < tw * hpw; i += kThreads) htab[i] = j.hp[(size_t)t.x0 * hpw + i];
     }
-    cp_async_wait<1>();  // this tile's rows have landed (the next tile's may still be in flight)
+    cp_async_wait<0>();  // this tile's rows have landed
     __syncthreads();
+    // the next tile's rows are requested now, into the other stage buffer (its last reader, pass 1 of the previous tile, is
+    // several barriers behind): they have passes 1-3 of this tile to arrive
+    if (tinfo[buf ^ 1].valid)
+      request_rows(jobs[tinfo[buf ^ 1].job], tinfo[buf ^ 1], smem + (buf ^ 1) * stage_bytes, rowoff[buf ^ 1]);
+    cp_async_commit();
 
     // ---- interleaved RGB: split the staged rows into planes (aligned rows, pitch Lq) so that pass 1 sees adjacent taps
     const uint8_t* rows_base = stage;
@@ -202,42 +220,53 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     // ---- pass 1: horizontal. Thread = (output column x, alignment class rho): the rows r = rho, rho+4, ... of a segment
     // share their misalignment modulo 4 when walked with a constant pitch, so the word offset and the funnel-shift amount of
     // the column's tap window are loop constants; per row: three aligned words, two funnel shifts, one dp2a per tap pair.
+    const int nseg = t.nseg;
     if (j.hb && j.hkp <= kMaxPairs) {
-      const int lanes_x = tw;                           // threads with the same rho
-      const int nrho = min(4, kThreads / lanes_x);      // classes handled at once (2 for a 112-column tile)
-      const int x = threadIdx.x % lanes_x, grp = threadIdx.x / lanes_x;
-      if (grp < nrho) {
+      // Thread = (output column x, row group): the column's taps (up to four int16 pairs, two sets for Pillow's split 22-bit
+      // taps) stay in registers; per row: the row's misalignment + the column's offset give an aligned word address and a funnel-
+      // shift amount, three aligned words -> two shifts -> the eight tap bytes, one dp2a per tap pair.
+      const int nrg = kThreads / tw;                    // row groups side by side (84 columns -> 3, 56 -> 4, 112 -> 2)
+      const int x = threadIdx.x % tw, grp = threadIdx.x / tw;
+      if (grp < nrg) {
         const int xo = xoff[x];
-        uint32_t kp[2][kMaxPairs];
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-          for (int k = 0; k < kMaxPairs; ++k) kp[s2][k] = (s2 < j.hsets && k < j.hkp) ? htab[x * hpw + s2 * j.hkp + k] : 0u;
-        const int round0 = 1 << (j.hprec - 1);
+        const uint32_t* kx = htab + x * hpw;
+        const int hkp = j.hkp;
         const bool split = j.hsets == 2;
-        for (int rho = grp; rho < 4; rho += nrho) {
-          for (int pl = 0; pl < planes; ++pl) {
-            const int sg = t.nseg == 3 ? pl : 0;
-            const uint8_t* segp = rows_base + (size_t)(aligned_rows ? pl : sg) * seg_rows * row_pitch_s;
-            for (int r = rho; r < rows_in; r += 4) {
-              const int boff = (aligned_rows ? 0 : rowoff[buf][sg * rows_in + r]) + xo;   // byte offset of the first tap in the staged row
-              const uint32_t a = smem_u32(segp + (size_t)r * row_pitch_s) + (uint32_t)(boff & ~3);
-              const int sh = (boff & 3) * 8;
-              const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
-              const uint32_t p = __funnelshift_r(w0, w1, sh), q = __funnelshift_r(w1, w2, sh);  // taps 0..3, 4..7
-              int acc = __dp2a_lo((int)kp[0][0], p, 0);
-              acc = __dp2a_hi((int)kp[0][1], p, acc);
-              acc = __dp2a_lo((int)kp[0][2], q, acc);
-              acc = __dp2a_hi((int)kp[0][3], q, acc);
-              if (split) {  // 22-bit taps = hi * 2^11 + lo, both halves int16: sum = (sum_hi << 11) + sum_lo, exactly
-                int lo = __dp2a_lo((int)kp[1][0], p, 0);
-                lo = __dp2a_hi((int)kp[1][1], p, lo);
-                lo = __dp2a_lo((int)kp[1][2], q, lo);
-                lo = __dp2a_hi((int)kp[1][3], q, lo);
-                acc = (acc << 11) + lo;
-              }
-              mid[pl * mid_plane + r * tw + x] = (uint8_t)sat_u8((acc + round0) >> j.hprec);
+        const uint32_t k0 = kx[0], k1 = hkp > 1 ? kx[1] : 0u, k2 = hkp > 2 ? kx[2] : 0u, k3 = hkp > 3 ? kx[3] : 0u;
+        const uint32_t l0 = split ? kx[hkp] : 0u, l1 = split && hkp > 1 ? kx[hkp + 1] : 0u, l2 = split && hkp > 2 ? kx[hkp + 2] : 0u,
+                       l3 = split && hkp > 3 ? kx[hkp + 3] : 0u;
+        const int prec = j.hprec, round0 = 1 << (prec - 1);
+        const int rstep = nrg * row_pitch_s, mstep = nrg * tw;
+        for (int pl = 0; pl < planes; ++pl) {
+          const int sg = nseg == 3 ? pl : 0;
+          const uint8_t* rp = rows_base + (size_t)((aligned_rows ? pl : sg) * seg_rows + grp) * row_pitch_s;
+          const uint8_t* rop = &rowoff[buf][sg * rows_in + grp];
+          uint8_t* mp = mid + pl * mid_plane + grp * tw + x;
+#pragma unroll 2
+          for (int r = grp; r < rows_in; r += nrg, rp += rstep, rop += nrg, mp += mstep) {
+            const int boff = (aligned_rows ? 0 : (int)*rop) + xo;   // byte offset of the column's first tap in the staged row
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(rp + (boff & ~3));
+            const int sh = (boff & 3) * 8;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t p = __funnelshift_r(w0, w1, sh), q = __funnelshift_r(w1, w2, sh);  // taps 0..3, 4..7
+            int acc;
+            if (!split) {
+              acc = dp2a_lo_su(k0, p, round0);
+              acc = dp2a_hi_su(k1, p, acc);
+              acc = dp2a_lo_su(k2, q, acc);
+              acc = dp2a_hi_su(k3, q, acc);
+            } else {  // 22-bit taps = hi * 2^11 + lo, both halves int16: sum = (sum_hi << 11) + sum_lo, exactly
+              int hi = dp2a_lo_su(k0, p, 0);
+              hi = dp2a_hi_su(k1, p, hi);
+              hi = dp2a_lo_su(k2, q, hi);
+              hi = dp2a_hi_su(k3, q, hi);
+              int lo = dp2a_lo_su(l0, p, round0);
+              lo = dp2a_hi_su(l1, p, lo);
+              lo = dp2a_lo_su(l2, q, lo);
+              lo = dp2a_hi_su(l3, q, lo);
+              acc = hi * 2048 + lo;
             }
+            *mp = (uint8_t)sat_u8(acc >> prec);
           }
         }
       }
@@ -246,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
       for (int i = threadIdx.x; i < planes * rows_in * tw; i += kThreads) {
         const int x = i % tw, rr = i / tw;
         const int pl = rr / rows_in, r = rr - pl * rows_in;
-        const int sg = t.nseg == 3 ? pl : 0;
+        const int sg = nseg == 3 ? pl : 0;
         const uint8_t* rowp = aligned_rows ? rows_base + (size_t)(pl * seg_rows + r) * row_pitch_s
                                            : rows_base + (size_t)(sg * rows_in + r) * row_pitch_s + rowoff[buf][sg * rows_in + r];
         int v;
@@ -263,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
               lo += px * (int)(int16_t)((k & 1) ? (w2 >> 16) : (w2 & 0xffff));
             }
           }
-          const int acc = j.hsets == 2 ? (hi << 11) + lo : hi;
+          const int acc = j.hsets == 2 ? hi * 2048 + lo : hi;
           v = sat_u8((acc + (1 << (j.hprec - 1))) >> j.hprec);
         } else {
           v = rowp[x];
@@ -292,23 +321,23 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
           for (int k = 0; 2 * k < cnt; ++k) {
             const uint32_t wa = lds_u32(a0 + (uint32_t)(2 * k * tw)), wb = lds_u32(a0 + (uint32_t)((2 * k + 1) * tw));  // row ymin+cnt may be one past: its tap is 0
             const uint32_t ab = __byte_perm(wa, wb, 0x5140), cd = __byte_perm(wa, wb, 0x7362);   // (a0 b0 a1 b1), (a2 b2 a3 b3)
-            const int k0 = (int)__ldg(kk + k);
-            hi[0] = __dp2a_lo(k0, ab, hi[0]);
-            hi[1] = __dp2a_hi(k0, ab, hi[1]);
-            hi[2] = __dp2a_lo(k0, cd, hi[2]);
-            hi[3] = __dp2a_hi(k0, cd, hi[3]);
+            const uint32_t k0 = __ldg(kk + k);
+            hi[0] = dp2a_lo_su(k0, ab, hi[0]);
+            hi[1] = dp2a_hi_su(k0, ab, hi[1]);
+            hi[2] = dp2a_lo_su(k0, cd, hi[2]);
+            hi[3] = dp2a_hi_su(k0, cd, hi[3]);
             if (j.vsets == 2) {
-              const int k1 = (int)__ldg(kk + j.vkp + k);
-              lo[0] = __dp2a_lo(k1, ab, lo[0]);
-              lo[1] = __dp2a_hi(k1, ab, lo[1]);
-              lo[2] = __dp2a_lo(k1, cd, lo[2]);
-              lo[3] = __dp2a_hi(k1, cd, lo[3]);
+              const uint32_t k1 = __ldg(kk + j.vkp + k);
+              lo[0] = dp2a_lo_su(k1, ab, lo[0]);
+              lo[1] = dp2a_hi_su(k1, ab, lo[1]);
+              lo[2] = dp2a_lo_su(k1, cd, lo[2]);
+              lo[3] = dp2a_hi_su(k1, cd, lo[3]);
             }
           }
           uint32_t packed = 0;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int acc = j.vsets == 2 ? (hi[e] << 11) + lo[e] : hi[e];
+            const int acc = j.vsets == 2 ? hi[e] * 2048 + lo[e] : hi[e];
             packed |= (uint32_t)sat_u8((acc + round0) >> j.vprec) << (8 * e);
           }
           *reinterpret_cast<uint32_t*>(res + (pl * kStrip + y) * tw + 4 * xg) = packed;
@@ -365,8 +394,10 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
 }
 
 struct AxisTable {
-  std::vector<int32_t> bounds, coeffs;
-  int ksize = 0, prec = 0, max_rows = 0;  // max_rows: input rows a 28-row output strip can touch
+  std::vector<int32_t> bounds;    // [out][2]: first input index, taps
+  std::vector<uint32_t> pairs;    // [out][kp * sets]: taps as int16 pairs (low half = even tap); 22-bit taps as hi set then lo set
+  int ksize = 0, prec = 0, kp = 0, sets = 1;
+  int max_rows = 0;               // input rows a 28-row output strip can touch
 };
 
 static std::map<std::tuple<int, int, int>, AxisTable>& table_cache() {
@@ -382,12 +413,28 @@ static int get_table(int in_size, int out_size, int mode, const AxisTable** out)
     AxisTable t;
     t.ksize = resample_ksize(in_size, out_size);
     t.bounds.resize((size_t)out_size * 2);
-    t.coeffs.resize((size_t)out_size * t.ksize);
-    int rc = resample_coeffs(in_size, out_size, mode, t.bounds.data(), t.coeffs.data(), &t.prec);
+    std::vector<int32_t> coeffs((size_t)out_size * t.ksize);
+    int rc = resample_coeffs(in_size, out_size, mode, t.bounds.data(), coeffs.data(), &t.prec);
     if (rc) return rc;
     for (int y0 = 0; y0 + kStrip <= out_size; y0 += kStrip) {
       int last = y0 + kStrip - 1;
       t.max_rows = std::max(t.max_rows, t.bounds[2 * last] + t.bounds[2 * last + 1] - t.bounds[2 * y0]);
+    }
+    // dp2a operands. ATen's taps are int16 already; Pillow's (22-bit precision) are split as c = hi * 2^11 + lo with
+    // lo in [0, 2047]: sum(c * p) = (sum(hi * p) << 11) + sum(lo * p) exactly, and both halves fit int16.
+    t.kp = (t.ksize + 1) / 2;
+    t.sets = mode == KOCR_RESIZE_PIL ? 2 : 1;
+    t.pairs.assign((size_t)out_size * t.kp * t.sets, 0u);
+    for (int o = 0; o < out_size; ++o) {
+      const int cnt = t.bounds[2 * o + 1];
+      for (int k = 0; k < cnt; ++k) {
+        const int32_t c = coeffs[(size_t)o * t.ksize + k];
+        const int32_t hi = t.sets == 2 ? (c >> 11) : c, lo = c & 2047;
+        if (hi < -32768 || hi > 32767) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: filter tap out of the int16 range");
+        uint32_t* row = &t.pairs[(size_t)o * t.kp * t.sets];
+        row[k >> 1] |= (uint32_t)(uint16_t)(int16_t)hi << (16 * (k & 1));
+        if (t.sets == 2) row[t.kp + (k >> 1)] |= (uint32_t)(uint16_t)lo << (16 * (k & 1));
+      }
     }
     it = cache.emplace(key, std::move(t)).first;
   }
@@ -414,24 +461,24 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   if ((reinterpret_cast<uintptr_t>(pixel_values) & 15) != 0)
     return fail(KOCR_ERR_INVALID, "kocr_preprocess: pixel_values must be 16-byte aligned");
 
-  // ---- plan on the host: sizes, filter banks (deduplicated), tiles
+  // ---- plan on the host: sizes, filter banks (deduplicated), tiles, shared-memory carve-up
   if (table_cache().size() > 256) table_cache().clear();  // bound the per-thread cache (pointers below stay valid)
   std::vector<PageJob> jobs(n_images);
-  struct Need { const AxisTable* t; size_t off_b, off_c; };
+  struct Need { size_t off_b, off_p; };
   std::map<const AxisTable*, Need> needs;
   size_t table_bytes = 0;
   auto want = [&](const AxisTable* t) {
     if (needs.count(t)) return;
-    Need n{t, table_bytes, 0};
+    Need n{table_bytes, 0};
     table_bytes += t->bounds.size() * 4;
-    n.off_c = table_bytes;
-    table_bytes += t->coeffs.size() * 4;
+    n.off_p = table_bytes;
+    table_bytes += t->pairs.size() * 4;
     needs[t] = n;
   };
   std::vector<const AxisTable*> ht(n_images, nullptr), vt(n_images, nullptr);
   int64_t tokens = 0;
-  int tiles = 0, max_mid = 0, max_res = 0;
-  const int kSmemBudget = 64 * 1024;
+  int tiles = 0;
+  int stage_bytes = 0, planar_bytes = 0, tab_bytes = 112 * 4, mid_bytes = 0, res_bytes = 0, max_tw = 0;
   for (int i = 0; i < n_images; ++i) {
     const KocrImage& im = images[i];
     if (!im.data || im.layout < 0 || im.layout > 2) return fail(KOCR_ERR_INVALID, "kocr_preprocess: bad image");
@@ -446,24 +493,53 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     j.in_h = im.height; j.in_w = im.width; j.layout = im.layout;
     j.src_bytes = (long long)im.height * im.width * (im.layout == KOCR_LAYOUT_GRAY ? 1 : 3);
     if (im.layout == KOCR_LAYOUT_CHW) { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = (long long)im.height * im.width; }
-    else if (im.layout == KOCR_LAYOUT_HWC) { j.pix_stride = 3; j.row_pitch = 3 * im.width; j.chan_stride = 1; }
+    else if (im.layout == KOCR_LAYOUT_HWC) { j.pix_stride = 3; j.row_pitch = 3 * im.width; j.chan_stride = 0; }
     else { j.pix_stride = 1; j.row_pitch = im.width; j.chan_stride = 0; }
     j.out_h = oh; j.out_w = ow;
     j.token_base = tokens;
     const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
-    if ((vt[i] ? 3 : 3) * rows_in > kMaxStageRows)
+    const int nseg = im.layout == KOCR_LAYOUT_CHW ? 3 : 1, planes = im.layout == KOCR_LAYOUT_GRAY ? 1 : 3;
+    if (3 * rows_in > 768)
       return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: vertical downscale factor too large for one tile");
-    int tw = 112;  // staged output tile: 16 tokens = 37.6 KB (bf16) / 75.3 KB (f32); keeps 3+ CTAs resident per SM
-    while (tw > kStrip && 3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > kSmemBudget) tw -= kStrip;
-    if (3 * tw * (rows_in + (vt[i] ? kStrip : 0)) > 200 * 1024)
-      return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: vertical downscale factor too large for one tile");
-    tw = std::min(tw, ow);
+    // shared memory of one CTA as a function of the tile width
+    const double scale = std::max(1.0, (double)im.width / ow);
+    const int elt = out_dtype == KOCR_DTYPE_BF16 ? 2 : 4;
+    struct Carve { int stage, planar, tab, mid, res, outb, total; };
+    auto carve = [&](int w) {
+      Carve c{};
+      // the widest span of input columns a tile can touch (a bound: the kernel works out the exact one per tile)
+      const int ncols = ht[i] ? (int)(w * scale) + 2 * ht[i]->ksize + 8 : w;
+      const int nvec = (15 + ncols * j.pix_stride + 15) >> 4;
+      c.stage = nseg * rows_in * (nvec + 1) * 16;
+      c.planar = im.layout == KOCR_LAYOUT_HWC ? 3 * rows_in * ((ncols + 12 + 3) & ~3) + 16 : 0;
+      c.tab = 112 * 4 + (ht[i] ? w * ht[i]->kp * ht[i]->sets * 4 : 0);
+      c.mid = planes * (rows_in + 1) * w + 16;
+      c.res = vt[i] ? planes * kStrip * w : 0;
+      c.outb = (w / kStrip) * 4 * kPatchDim * elt;
+      c.total = 2 * c.stage + c.planar + c.tab + c.mid + c.res + c.outb + 256;
+      return c;
+    };
+    // default tile: 84 columns = 12 tokens (28 KB of bf16 output); ~61 KB per CTA for a letter page, three CTAs per SM. Strong
+    // downscales and the f32 drop-in output take narrower tiles; KOCR_PRE_TW overrides the default for experiments.
+    static const int tw_default = [] {
+      const char* e = getenv("KOCR_PRE_TW");
+      const int v = e ? atoi(e) : 84;
+      return (v >= kStrip && v <= 112 && v % kStrip == 0) ? v : 84;
+    }();
+    int tw = std::min(tw_default, ow);
+    while (tw > kStrip && carve(tw).total > 72 * 1024) tw -= kStrip;
+    const Carve cv = carve(tw);
+    if (cv.total > kMaxDynSmem) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: downscale factor too large for one tile");
     j.tile_w = tw;
     j.tiles_x = (ow + tw - 1) / tw;
     j.tile_base = tiles;
     tiles += j.tiles_x * (oh / kStrip);
-    max_mid = std::max(max_mid, 3 * tw * rows_in);
-    if (vt[i]) max_res = std::max(max_res, 3 * tw * kStrip);
+    max_tw = std::max(max_tw, tw);
+    stage_bytes = std::max(stage_bytes, cv.stage);
+    planar_bytes = std::max(planar_bytes, cv.planar);
+    tab_bytes = std::max(tab_bytes, cv.tab);
+    mid_bytes = std::max(mid_bytes, cv.mid);
+    res_bytes = std::max(res_bytes, cv.res);
     grid_thw_out[3 * i] = 1;
     grid_thw_out[3 * i + 1] = oh / 14;
     grid_thw_out[3 * i + 2] = ow / 14;
@@ -471,7 +547,16 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   }
   if (tokens > capacity_rows)
     return fail(KOCR_ERR_INVALID, "kocr_preprocess: pixel_values buffer too small for this batch");
-  max_mid = (max_mid + 15) & ~15;
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  stage_bytes = up(stage_bytes, 16);
+  const int planar_off = 2 * stage_bytes;
+  const int tab_off = planar_off + up(planar_bytes, 16);
+  const int mid_off = tab_off + up(tab_bytes, 16);
+  const int res_off = mid_off + up(mid_bytes, 16);
+  const int out_off = up(res_off + res_bytes, 128);
+  const int out_bytes = (max_tw / kStrip) * 4 * kPatchDim * (out_dtype == KOCR_DTYPE_BF16 ? 2 : 4);
+  const int smem = out_off + out_bytes;
+  if (smem > kMaxDynSmem) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: tile does not fit in shared memory");
 
   // ---- stage tables + jobs
   const size_t jobs_off = (table_bytes + 15) & ~size_t(15);
@@ -485,19 +570,19 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
   uint8_t* db = static_cast<uint8_t*>(ctx->d_slot[slot]);
   for (auto& kv : needs) {
     memcpy(hb + kv.second.off_b, kv.first->bounds.data(), kv.first->bounds.size() * 4);
-    memcpy(hb + kv.second.off_c, kv.first->coeffs.data(), kv.first->coeffs.size() * 4);
+    memcpy(hb + kv.second.off_p, kv.first->pairs.data(), kv.first->pairs.size() * 4);
   }
   for (int i = 0; i < n_images; ++i) {
     PageJob& j = jobs[i];
     if (ht[i]) {
       j.hb = reinterpret_cast<const int32_t*>(db + needs[ht[i]].off_b);
-      j.hc = reinterpret_cast<const int32_t*>(db + needs[ht[i]].off_c);
-      j.hk = ht[i]->ksize; j.hprec = ht[i]->prec;
+      j.hp = reinterpret_cast<const uint32_t*>(db + needs[ht[i]].off_p);
+      j.hkp = ht[i]->kp; j.hsets = ht[i]->sets; j.hprec = ht[i]->prec;
     }
     if (vt[i]) {
       j.vb = reinterpret_cast<const int32_t*>(db + needs[vt[i]].off_b);
-      j.vc = reinterpret_cast<const int32_t*>(db + needs[vt[i]].off_c);
-      j.vk = vt[i]->ksize; j.vprec = vt[i]->prec;
+      j.vp = reinterpret_cast<const uint32_t*>(db + needs[vt[i]].off_p);
+      j.vkp = vt[i]->kp; j.vsets = vt[i]->sets; j.vprec = vt[i]->prec;
     }
   }
   memcpy(hb + jobs_off, jobs.data(), sizeof(PageJob) * n_images);
@@ -508,36 +593,24 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
     return rc;
   }
 
-  int max_coef = 0;
-  for (int i = 0; i < n_images; ++i)
-    if (ht[i]) max_coef = std::max(max_coef, ht[i]->ksize * jobs[i].tile_w * 4);
-  int max_tw = 0;
-  for (int i = 0; i < n_images; ++i) max_tw = std::max(max_tw, jobs[i].tile_w);
-  const int coef_off = (max_mid + max_res + 15) & ~15;
-  const int out_off = (coef_off + max_coef + 127) & ~127;
-  int stage_bytes = 0;
-  for (int i = 0; i < n_images; ++i) {
-    const PageJob& j = jobs[i];
-    const int rows_in = vt[i] ? vt[i]->max_rows : kStrip;
-    const double scale = std::max(1.0, (double)j.in_w / j.out_w);
-    const int ncols = (int)(j.tile_w * scale) + 2 * (ht[i] ? ht[i]->ksize : 0) + 8;  // generous bound on the tap span
-    const int lp = ((ncols * j.pix_stride + 6) & ~3) + 4;
-    stage_bytes = std::max(stage_bytes, ((j.layout == KOCR_LAYOUT_CHW ? 3 : 1) * rows_in + kRB) * lp);  // + padding rows
+  // persistent CTAs: as many as are resident at once (each prefetches its next tile while it works on the current one)
+  int occ = 0;
+  if (out_dtype == KOCR_DTYPE_BF16) {
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<true>), kMaxDynSmem))) return rc;
+    KOCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, preprocess_kernel<true>, kThreads, smem));
+  } else {
+    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<false>), kMaxDynSmem))) return rc;
+    KOCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, preprocess_kernel<false>, kThreads, smem));
   }
-  const int out_bytes = (max_tw / kStrip) * 4 * kPatchDim * (out_dtype == KOCR_DTYPE_BF16 ? 2 : 4);
-  const int smem = out_off + std::max(out_bytes, stage_bytes);
-  if (smem > kMaxDynSmem) return fail(KOCR_ERR_UNSUPPORTED, "kocr_preprocess: tile does not fit in shared memory");
-  const int grid = std::min(tiles, ctx->num_sms * 8);
+  const int grid = std::min(tiles, ctx->num_sms * std::max(occ, 1));
   const PageJob* d_jobs = reinterpret_cast<const PageJob*>(db + jobs_off);
   ProfScope ps(ctx, kProfPreprocess, stream);
   if (out_dtype == KOCR_DTYPE_BF16) {
-    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<true>), kMaxDynSmem))) return rc;
-    preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                              pixel_values, max_mid, coef_off, out_off);
+    preprocess_kernel<true><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode], pixel_values,
+                                                              stage_bytes, planar_off, tab_off, mid_off, res_off, out_off);
   } else {
-    if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&preprocess_kernel<false>), kMaxDynSmem))) return rc;
-    preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode],
-                                                               pixel_values, max_mid, coef_off, out_off);
+    preprocess_kernel<false><<<grid, kThreads, smem, stream>>>(d_jobs, n_images, tiles, ctx->d_lut[resize_mode], pixel_values,
+                                                               stage_bytes, planar_off, tab_off, mid_off, res_off, out_off);
   }
   KOCR_LAUNCH_CHECK("preprocess_kernel");
   return KOCR_OK;

@@ -61,10 +61,13 @@ struct Tower {
   int rope_max_pos = 0;
   int32_t* d_qkv_perm = nullptr;
   int32_t* d_gu_perm = nullptr;
+  int32_t* d_id_perm = nullptr;  // identity over D rows (down_proj is only re-pitched)
   std::set<std::string> loaded;
   bool folded = false;  // norm1/norm2 have been folded into the qkv / fc1 weights (kocr_tower_finalize)
   int stat_slots = 0;   // partial-statistics slots per row = 2 * ceil(D / 256)
   std::vector<void*> allocs;
+  void* tmp = nullptr;  // weight-conversion scratch (set_weight), released by finalize
+  size_t tmp_cap = 0;
 
   template <typename T>
   int alloc(T** p, size_t n, bool zero = false) {
@@ -292,6 +295,10 @@ int kocr_tower_create(KocrCtx* ctx_, const KocrTowerConfig* cfg, KocrTower** out
     for (int j = 0; j < Fp; ++j) gp[j] = j < t->F ? j : -1;
     if (!rc) rc = t->alloc(&t->d_gu_perm, Fp);
     if (!rc) KOCR_CUDA_CHECK(cudaMemcpy(t->d_gu_perm, gp.data(), gp.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int32_t> idp(D);
+    for (int r = 0; r < D; ++r) idp[r] = r;
+    if (!rc) rc = t->alloc(&t->d_id_perm, D);
+    if (!rc) KOCR_CUDA_CHECK(cudaMemcpy(t->d_id_perm, idp.data(), idp.size() * 4, cudaMemcpyHostToDevice));
   }
   if (rc) {
     for (void* p : t->allocs) cudaFree(p);
@@ -309,6 +316,7 @@ void kocr_tower_destroy(KocrTower* tower) {
   cudaDeviceSynchronize();
   for (void* p : t->allocs) cudaFree(p);
   if (t->rope_cs) cudaFree(t->rope_cs);
+  if (t->tmp) cudaFree(t->tmp);
   for (Plan* p : t->plans) {
     if (p->d) cudaFree(p->d);
     if (p->used) cudaEventDestroy(p->used);
@@ -337,14 +345,18 @@ int kocr_tower_set_weight(KocrTower* tower, const char* name_, const void* data,
   auto permuted = [&](void* dst, int ddt, int64_t src_rows, int64_t cols, const int32_t* perm, int64_t dst_rows,
                       int64_t dst_ld) -> int {
     if (n != src_rows * cols) return bad_shape();
-    void* tmp = nullptr;
     const int elt = ddt == KOCR_DTYPE_F32 ? 4 : 2;
-    KOCR_CUDA_CHECK(cudaMalloc(&tmp, (size_t)n * elt));
-    int rc = launch_convert(data, dtype, tmp, ddt, n, st);
-    if (!rc) rc = launch_permute_rows(tmp, dst, perm, dst_rows, cols, cols, dst_ld, elt, st);
-    cudaStreamSynchronize(st);
-    cudaFree(tmp);
-    return rc;
+    if (t->tmp_cap < (size_t)n * elt) {  // one conversion buffer for the whole load (grown, never per tensor), freed at finalize
+      KOCR_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (t->tmp) cudaFree(t->tmp);
+      t->tmp = nullptr;
+      t->tmp_cap = 0;
+      KOCR_CUDA_CHECK(cudaMalloc(&t->tmp, (size_t)n * elt));
+      t->tmp_cap = (size_t)n * elt;
+    }
+    int rc = launch_convert(data, dtype, t->tmp, ddt, n, st);
+    if (!rc) rc = launch_permute_rows(t->tmp, dst, perm, dst_rows, cols, cols, dst_ld, elt, st);
+    return rc;  // stream-ordered: the next tensor's conversion follows this permute on the same stream
   };
   int rc = KOCR_ERR_INVALID;
   if (name == "patch_embed.proj.weight") {
@@ -390,13 +402,7 @@ int kocr_tower_set_weight(KocrTower* tower, const char* name_, const void* data,
     // down_proj [D, F] -> [D, Fp] (zero padded K): identity row "permutation" with a wider destination pitch
     else if (t->q25 && k == "mlp.down_proj.weight") {
       if (n != (int64_t)D * F) return bad_shape();
-      std::vector<int32_t> id(D);
-      for (int r = 0; r < D; ++r) id[r] = r;
-      int32_t* d_id = nullptr;
-      KOCR_CUDA_CHECK(cudaMalloc(&d_id, D * 4));
-      KOCR_CUDA_CHECK(cudaMemcpy(d_id, id.data(), D * 4, cudaMemcpyHostToDevice));
-      rc = permuted(b.w_fc2, KOCR_DTYPE_BF16, D, F, d_id, D, Fp);
-      cudaFree(d_id);
+      rc = permuted(b.w_fc2, KOCR_DTYPE_BF16, D, F, t->d_id_perm, D, Fp);
     } else if (t->q25 && k == "mlp.down_proj.bias") rc = plain(b.b_fc2, KOCR_DTYPE_F32, D);
     else return fail(KOCR_ERR_INVALID, "unknown weight " + name);
   } else {
@@ -430,6 +436,9 @@ int kocr_tower_finalize(KocrTower* tower) {
       if (rc) return rc;
     }
     KOCR_CUDA_CHECK(cudaStreamSynchronize(0));
+    if (t->tmp) cudaFree(t->tmp);
+    t->tmp = nullptr;
+    t->tmp_cap = 0;
     t->folded = true;
   }
   return KOCR_OK;

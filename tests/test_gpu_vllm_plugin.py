@@ -87,7 +87,7 @@ def test_plugin_inside_live_engine(tmp_path, arch):
     assert mine["visual_class"] == "KarantaVllmVisual"
     assert mine.get("image_processor_class", "KarantaImageProcessor") == "KarantaImageProcessor"
     assert stock.get("image_processor_class", "Qwen2VLImageProcessor") != "KarantaImageProcessor"
-    assert mine["emb_shape"] == stock["emb_shape"] == [30 * 24 // 4, 64]      # 420x322 -> 420x336 -> grid 30x24
+    assert mine["emb_shape"] == stock["emb_shape"] == [30 * 24 // 4, 256]      # 420x322 -> 420x336 -> grid 30x24
     a, b = mine_emb.astype(np.float64).ravel(), stock_emb.astype(np.float64).ravel()
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
     rel = float(np.abs(a - b).max() / np.abs(b).max())

@@ -28,7 +28,7 @@ def hf_processor(min_pixels=3136, max_pixels=12845056):
 def write_tiny_checkpoint(path, arch="qwen2_vl", min_pixels=3136, max_pixels=12845056):
     """A checkpoint DIRECTORY (config.json, tokenizer, processor configs, chat template; no weights - vLLM's
     load_format="dummy" or a caller's own state dict supplies them) of a very small Qwen2-VL / Qwen2.5-VL whose vision tower
-    has the real head_dim (80): depth 2, embed_dim 160, 2 heads, merged into a 64-wide two-layer language model."""
+    has the real head_dim (80): depth 2, embed_dim 160, 2 heads, merged into a 256-wide two-layer language model (head_dim 128)."""
     import json
     import os
     from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor
@@ -36,21 +36,22 @@ def write_tiny_checkpoint(path, arch="qwen2_vl", min_pixels=3136, max_pixels=128
     os.makedirs(path, exist_ok=True)
     tok = tiny_tokenizer()
     vocab = tok.get_vocab()
-    text = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
-                vocab_size=64, max_position_embeddings=8192, rope_scaling={"type": "mrope", "mrope_section": [2, 3, 3]},
+    # head_dim 128 like the real models (vLLM's FA4 text attention does not take tiny head sizes)
+    text = dict(hidden_size=256, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+                vocab_size=64, max_position_embeddings=8192, rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]},
                 tie_word_embeddings=False)
     ids = dict(image_token_id=vocab["<|image_pad|>"], video_token_id=vocab["<|video_pad|>"], vision_start_token_id=vocab["<|vision_start|>"],
                vision_end_token_id=vocab["<|vision_end|>"], bos_token_id=vocab["<|endoftext|>"], eos_token_id=vocab["<|im_end|>"])
     if arch == "qwen2_vl":
         from transformers.models.qwen2_vl.configuration_qwen2_vl import Qwen2VLConfig
         from transformers.models.qwen2_vl.processing_qwen2_vl import Qwen2VLProcessor as Proc
-        cfg = Qwen2VLConfig(text_config=text, vision_config=dict(depth=2, embed_dim=160, hidden_size=64, num_heads=2, mlp_ratio=4), **ids)
+        cfg = Qwen2VLConfig(text_config=text, vision_config=dict(depth=2, embed_dim=160, hidden_size=256, num_heads=2, mlp_ratio=4), **ids)
         cfg.architectures = ["Qwen2VLForConditionalGeneration"]
     else:
         from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
         from transformers.models.qwen2_5_vl.processing_qwen2_5_vl import Qwen2_5_VLProcessor as Proc
         cfg = Qwen2_5_VLConfig(text_config=text, vision_config=dict(depth=2, hidden_size=160, intermediate_size=428, num_heads=2,
-                                                                     out_hidden_size=64, fullatt_block_indexes=[1], window_size=112), **ids)
+                                                                     out_hidden_size=256, fullatt_block_indexes=[1], window_size=112), **ids)
         cfg.architectures = ["Qwen2_5_VLForConditionalGeneration"]
     cfg.torch_dtype = "bfloat16"
     cfg.save_pretrained(path)
