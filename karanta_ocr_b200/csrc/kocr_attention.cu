@@ -65,7 +65,24 @@ static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over a
 #define KOCR_POLY_EVERY 4
 #endif
 static constexpr int kPolyEvery = KOCR_POLY_EVERY;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
-static constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the row max grows by more than 2^8
+#ifndef KOCR_PROBE
+#define KOCR_PROBE 0   // timing probes (wrong results): bit 0 no exponentials, bit 1 no row max, bit 2 no TMEM score load, bit 3 no P store
+#endif
+static constexpr int kProbe = KOCR_PROBE;
+static constexpr float kRescaleThreshold = 8.0f;
+
+// Timeline trace of one CTA (variant builds with -DKOCR_TRACE only): lane 0 of every warp stamps clock64 at fixed points of each
+// sub-step; tools/attn_trace.py reads the stamps back and prints where each warp's time goes.
+#ifdef KOCR_TRACE
+static constexpr int kTraceSubs = 96, kTracePts = 12, kTraceWarps = 12;
+__device__ long long g_attn_trace[kTraceWarps][kTraceSubs][kTracePts];
+#define KOCR_STAMP(i, pt)                                                                                     \
+  do {                                                                                                        \
+    if (trace_on && lane == 0 && (i) < kTraceSubs) g_attn_trace[warp][(i)][(pt)] = clock64();                \
+  } while (0)
+#else
+#define KOCR_STAMP(i, pt) do {} while (0)
+#endif  // log2 units: rescale O only when the row max grows by more than 2^8
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -180,6 +197,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int lane = threadIdx.x & 31;
   const AttnWork w = work[blockIdx.x];
   const int head = blockIdx.y;
+#ifdef KOCR_TRACE
+  const bool trace_on = !kWin && blockIdx.x == 13 && blockIdx.y == 5;
+#endif
   const int n_sub = (w.kv_len + kSub - 1) / kSub;           // score sub-steps = K/V tiles
   const int col_q = head * 3 * kHd, col_k = col_q + kHd, col_v = col_q + 2 * kHd;
 
@@ -270,7 +290,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_pv = [&](int i) {
         const int s = i % kKvStages;
         mbar_wait(&v_full[s], (i / kKvStages) & 1);
+        KOCR_STAMP(i, 3);
         mbar_wait(&p_full[t * 2 + (i & 1)], (i >> 1) & 1);
+        KOCR_STAMP(i, 4);
         tc_fence_after();
         const uint32_t va = v_lo + s * (kKvTileBytes >> 4);
         const uint32_t pa = tmem_u + Shape::s_col(t, i & 1);
@@ -284,8 +306,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       issue_s(0);
       if (n_sub_u > 1) issue_s(1);
       for (int i = 0; i < n_sub_u; ++i) {
+        KOCR_STAMP(i, 0);
         issue_pv(i);
+        KOCR_STAMP(i, 1);
         if (i + 2 < n_sub_u) issue_s(i + 2);
+        KOCR_STAMP(i, 2);
       }
     }
   } else {
@@ -316,13 +341,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int b = i & 1;                    // S/P buffer and barrier slot of this sub-step
       const uint32_t ph = (i >> 1) & 1;      // phase of s_full / p_full / o_done[b] for this sub-step
       const uint32_t t_s = tmem_base + Shape::s_col(t, b) + lane_off;
+      KOCR_STAMP(i, 0);
       mbar_wait(&s_full[t * 2 + b], ph);
+      KOCR_STAMP(i, 1);
       tc_fence_after();
       uint32_t sr[kSub];
-      tmem_ld_x32(t_s, sr);
-      tmem_ld_x32(t_s + 32, sr + 32);
-      if constexpr (kSub == 80) tmem_ld_x16(t_s + 64, sr + 64);
-      tc_wait_ld();
+      if (kProbe & 4) {
+#pragma unroll
+        for (int c = 0; c < kSub; ++c) sr[c] = __float_as_uint(-0.01f * (float)((c * 7 + i + lane) & 63));
+      } else {
+        tmem_ld_x32(t_s, sr);
+        tmem_ld_x32(t_s + 32, sr + 32);
+        if constexpr (kSub == 80) tmem_ld_x16(t_s + 64, sr + 64);
+        tc_wait_ld();
+      }
+      KOCR_STAMP(i, 2);
       const int c0 = i * kSub;  // key index (relative to kv_begin) of the first column
       if (kWin) {
         const int c_lo = w_lo - c0, c_hi = w_hi - c0;  // valid columns: [c_lo, c_hi)
@@ -351,6 +384,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       float mx = mxa[0];
 #pragma unroll
       for (int g = 1; g < kSub / 16; ++g) mx = fmaxf(mx, mxa[g]);
+      if (kProbe & 2) mx = 0.f;
       float alpha = 1.0f;
       const bool grow = mx > m_ref + kRescaleThreshold;  // true on the first sub-step with an unmasked key (m_ref = -inf)
       if (grow) {
@@ -360,7 +394,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // p = 2^(s - m): packed f32x2 subtract and independent packed row-sum accumulators
       // (a row whose keys so far are all masked still has m_ref = -inf: subtract 0 so its p are 2^-inf = 0, not NaN)
       float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      KOCR_STAMP(i, 3);
       if (kPP) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");  // the exponents depend on neg_m
+      KOCR_STAMP(i, 4);
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[kSub / 2];
@@ -368,7 +404,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int c = 0; c < kSub / 2; ++c) {
         const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
         uint64_t p2;
-        if (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) {
+        if (kProbe & 1) {
+          p2 = x2;
+        } else if (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) {
           p2 = ex2_poly_f32x2(x2);  // FMA/ALU pipes: relieves the MUFU unit
         } else {
           float x0, x1;
@@ -392,12 +430,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         sum = (a0 + a1) + (b0 + b1);
       }
       l = l * alpha + sum;
-      tmem_st_x16(t_s, pk);
-      tmem_st_x16(t_s + 16, pk + 16);
-      if constexpr (kSub == 80) tmem_st_x8(t_s + 32, pk + 32);
+      KOCR_STAMP(i, 5);
+      if (!(kProbe & 8)) {
+        tmem_st_x16(t_s, pk);
+        tmem_st_x16(t_s + 16, pk + 16);
+        if constexpr (kSub == 80) tmem_st_x8(t_s + 32, pk + 32);
+      } else {
+        uint32_t x = 0;  // keeps the conversions alive
+#pragma unroll
+        for (int c = 0; c < kSub / 2; ++c) x ^= pk[c];
+        asm volatile("" ::"r"(x));
+      }
       // P.V completions are signalled on one barrier per S/P buffer, o_done[t][b]; every completion is observed, in
       // order - P_{i-2} V here, normally long done - so a parity wait stays unambiguous.
+      KOCR_STAMP(i, 6);
       if (i > 1) mbar_wait(&o_done[t * 2 + b], ph ^ 1);
+      KOCR_STAMP(i, 7);
       if (i > 0) {
         // O_t holds P V of sub-steps < i relative to the old reference; bring it to the new one before P_i V is added. P_{i-1} V is waited for only when O really has to be rescaled.
         if (__any_sync(0xffffffffu, grow)) {
@@ -412,8 +460,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
       }
       tc_wait_st();
+      KOCR_STAMP(i, 8);
       tc_fence_before();
       mbar_arrive(&p_full[t * 2 + b]);
+      KOCR_STAMP(i, 9);
     }
     // ---- epilogue: O / l -> bf16 -> out[row, head*80 ...]
     mbar_wait(&o_done[t * 2 + ((n_sub - 1) & 1)], ((n_sub - 1) >> 1) & 1);  // the last P.V (the pipe completes in order)
@@ -526,3 +576,10 @@ extern "C" int kocr_op_attention(KocrCtx* ctx_, const void* qkv, void* out, cons
   return launch_attention(ctx, qkv, out, static_cast<const AttnWork*>(d_work), (int)work.size(), num_heads,
                           cu_seqlens_host[n_seqs], stream, nullptr);
 }
+
+#ifdef KOCR_TRACE
+extern "C" __attribute__((visibility("default"))) int kocr_debug_attn_trace(void* dst, int64_t bytes) {
+  if (bytes < (int64_t)sizeof(long long) * kTraceWarps * kTraceSubs * kTracePts) return KOCR_ERR_INVALID;
+  return cudaMemcpyFromSymbol(dst, g_attn_trace, sizeof(long long) * kTraceWarps * kTraceSubs * kTracePts) == cudaSuccess ? KOCR_OK : KOCR_ERR_CUDA;
+}
+#endif

@@ -45,12 +45,14 @@ struct PageJob {
   int out_h, out_w;
   int hkp, hsets, hprec, vkp, vsets, vprec;  // pairs per output, 1 set (int16 taps) or 2 (hi / lo halves of 22-bit taps)
   int tile_w, tiles_x, tile_base;
+  int hcols;  // output columns per thread in the horizontal pass: 4 or 2 when their tap windows start within 4 input pixels of each other, else 1
 };
 
 struct TileInfo {
   int job, valid;
   int y0, x0, tw, r0, rows_in, xin0, ncols_in;
   int nseg, planes, Lp, nvec;   // staged segments (3 planar / 1), filtered planes (1 gray / 3), staged row pitch, vectors per row
+  int lg_lpr;                   // log2 of the lanes that share one staged row in request_rows (>= nvec of them)
   long long n0;                 // first token of the tile
 };
 
@@ -129,6 +131,7 @@ __device__ void plan_tile(const PageJob* __restrict__ jobs, int n_jobs, int tile
   // a staged row = the 16-byte vectors that cover its bytes, plus 16 bytes of slack for the passes' whole-word reads
   t.nvec = (15 + t.ncols_in * j.pix_stride + 15) >> 4;
   t.Lp = (t.nvec + 1) * 16;
+  t.lg_lpr = 32 - __clz(t.nvec - 1);  // nvec >= 2
   t.n0 = j.token_base + ((long long)sy * (j.out_w / kStrip) + t.x0 / kStrip) * 4;
 }
 
@@ -138,15 +141,101 @@ __device__ __forceinline__ void request_rows(const PageJob& j, const TileInfo& t
   const int nrows = t.nseg * t.rows_in;
   const uintptr_t img_end = (reinterpret_cast<uintptr_t>(j.src) + (uintptr_t)j.src_bytes + 15) & ~uintptr_t(15);
   const uint32_t stage_u32 = smem_u32(stage);
-  const int total = nrows * t.nvec;
-  for (int i = threadIdx.x; i < total; i += kThreads) {
-    const int row = i / t.nvec, v = i - row * t.nvec;
-    const int sg = row / t.rows_in, r = row - sg * t.rows_in;
-    const uintptr_t p = reinterpret_cast<uintptr_t>(j.src) + (uintptr_t)(sg * j.chan_stride) + (uintptr_t)((long long)(t.r0 + r) * j.row_pitch) +
-                        (uintptr_t)((long long)t.xin0 * j.pix_stride);
+  const int lg = t.lg_lpr, nvec = t.nvec, rows_in = t.rows_in;
+  // a power-of-two group of lanes per row: row and vector index are a shift and a mask (no integer division on this path)
+  const int v = threadIdx.x & ((1 << lg) - 1);
+  if (v >= nvec) return;
+  const uintptr_t col0 = reinterpret_cast<uintptr_t>(j.src) + (uintptr_t)((long long)t.xin0 * j.pix_stride);
+  for (int row = threadIdx.x >> lg; row < nrows; row += kThreads >> lg) {
+    const int sg = (row >= rows_in) + (row >= 2 * rows_in), r = row - sg * rows_in;
+    const uintptr_t p = col0 + (uintptr_t)(sg * j.chan_stride) + (uintptr_t)((long long)(t.r0 + r) * j.row_pitch);
     const uintptr_t a = (p & ~uintptr_t(15)) + 16u * (uintptr_t)v;
     if (v == 0) rowoff[row] = (uint8_t)(p & 15);
     if (a < img_end) cp_async16(stage_u32 + (uint32_t)(row * t.Lp + v * 16), reinterpret_cast<const void*>(a));
+  }
+}
+
+// Two s32 -> saturated u8, packed under the upper half of c: d = sat(lo) | sat(hi) << 8 | c << 16
+__device__ __forceinline__ uint32_t pack_sat_u8(int hi, int lo, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t shf_r_clamp(uint32_t lo, uint32_t hi, uint32_t sh) {
+  uint32_t d;
+  asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sh));
+  return d;
+}
+
+// Horizontal pass, NC adjacent output columns per thread. Their tap windows start within four input pixels of each other
+// (any resize up to ~1.3x down: the host checks it per page), so one row costs four aligned words and three funnel shifts that
+// bring the first column's window to byte 0, then per column two clamped shifts by its own (loop-constant) offset, one dp2a per tap
+// pair and a shift; the NC results leave as one packed store. Rows are walked with one flat index over (plane, row).
+template <int NC, bool kSplit>
+__device__ __forceinline__ void pass1_multi(const PageJob& j, const TileInfo& t, const uint8_t* rows_base, int row_pitch_s, int seg_rows,
+                                            bool aligned_rows, const uint8_t* rowoff, const int32_t* xoff, const uint32_t* htab,
+                                            uint8_t* mid, int mid_plane) {
+  const int tw = t.tw, rows_in = t.rows_in, planes = t.planes, nseg = t.nseg;
+  const int ng = tw / NC;                            // column groups
+  const int nrg = kThreads / ng;                     // row slices side by side
+  const int g = threadIdx.x % ng, grp = threadIdx.x / ng;
+  if (grp >= nrg) return;
+  const int hkp = j.hkp, hpw = hkp * j.hsets;
+  const bool four = hkp > 3;
+  const int xo0 = xoff[NC * g];
+  uint32_t dsh[NC], k[NC][4], l[NC][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    dsh[c] = (uint32_t)(xoff[NC * g + c] - xo0) * 8u;   // 0, 8, ... 32
+    const uint32_t* kx = htab + (NC * g + c) * hpw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      k[c][i] = i < hkp ? kx[i] : 0u;
+      l[c][i] = (kSplit && i < hkp) ? kx[hkp + i] : 0u;
+    }
+  }
+  const int prec = j.hprec, round0 = 1 << (prec - 1);
+  const int total = planes * rows_in;
+#pragma unroll 2
+  for (int it = grp; it < total; it += nrg) {
+    const int pl = (it >= rows_in) + (it >= 2 * rows_in), r = it - pl * rows_in;
+    const int srow = (aligned_rows ? pl : (nseg == 3 ? pl : 0)) * seg_rows + r;
+    const int boff = (aligned_rows ? 0 : (int)rowoff[(nseg == 3 ? pl : 0) * rows_in + r]) + xo0;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rows_base + (size_t)srow * row_pitch_s + (boff & ~3));
+    const uint32_t sh = (uint32_t)(boff & 3) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+    int o[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint32_t p = shf_r_clamp(v0, v1, dsh[c]), q = shf_r_clamp(v1, v2, dsh[c]);  // taps 0..3, 4..7 of column c
+      int acc;
+      if (!kSplit) {
+        acc = dp2a_lo_su(k[c][0], p, round0);
+        acc = dp2a_hi_su(k[c][1], p, acc);
+        acc = dp2a_lo_su(k[c][2], q, acc);
+        if (four) acc = dp2a_hi_su(k[c][3], q, acc);
+      } else {  // 22-bit taps = hi * 2^11 + lo, both halves int16: sum = (sum_hi << 11) + sum_lo, exactly
+        int hi = dp2a_lo_su(k[c][0], p, 0);
+        hi = dp2a_hi_su(k[c][1], p, hi);
+        hi = dp2a_lo_su(k[c][2], q, hi);
+        int lo = dp2a_lo_su(l[c][0], p, round0);
+        lo = dp2a_hi_su(l[c][1], p, lo);
+        lo = dp2a_lo_su(l[c][2], q, lo);
+        if (four) {
+          hi = dp2a_hi_su(k[c][3], q, hi);
+          lo = dp2a_hi_su(l[c][3], q, lo);
+        }
+        acc = hi * 2048 + lo;
+      }
+      o[c] = acc >> prec;
+    }
+    uint8_t* mp = mid + pl * mid_plane + r * tw + NC * g;
+    if (NC == 4) {
+      *reinterpret_cast<uint32_t*>(mp) = pack_sat_u8(o[1], o[0], pack_sat_u8(o[NC - 1], o[NC - 2], 0u));
+    } else {
+      *reinterpret_cast<uint16_t*>(mp) = (uint16_t)pack_sat_u8(o[1], o[0], 0u);
+    }
   }
 }
 
@@ -204,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     bool aligned_rows = false;
     if (j.layout == KOCR_LAYOUT_HWC) {
       uint8_t* planar = smem + planar_off;
-      const int Lq = (t.ncols_in + 12 + 3) & ~3;
+      const int Lq = (t.ncols_in + 20 + 3) & ~3;
       for (int i = threadIdx.x; i < rows_in * t.ncols_in; i += kThreads) {
         const int r = i / t.ncols_in, x = i - r * t.ncols_in;
         const uint8_t* p = stage + r * t.Lp + rowoff[buf][r] + 3 * x;
@@ -221,7 +310,16 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     // share their misalignment modulo 4 when walked with a constant pitch, so the word offset and the funnel-shift amount of
     // the column's tap window are loop constants; per row: three aligned words, two funnel shifts, one dp2a per tap pair.
     const int nseg = t.nseg;
-    if (j.hb && j.hkp <= kMaxPairs) {
+    if (j.hb && j.hkp <= kMaxPairs && j.hcols > 1) {
+      const uint8_t* ro = rowoff[buf];
+      if (j.hcols == 4) {
+        if (j.hsets == 2) pass1_multi<4, true>(j, t, rows_base, row_pitch_s, seg_rows, aligned_rows, ro, xoff, htab, mid, mid_plane);
+        else pass1_multi<4, false>(j, t, rows_base, row_pitch_s, seg_rows, aligned_rows, ro, xoff, htab, mid, mid_plane);
+      } else {
+        if (j.hsets == 2) pass1_multi<2, true>(j, t, rows_base, row_pitch_s, seg_rows, aligned_rows, ro, xoff, htab, mid, mid_plane);
+        else pass1_multi<2, false>(j, t, rows_base, row_pitch_s, seg_rows, aligned_rows, ro, xoff, htab, mid, mid_plane);
+      }
+    } else if (j.hb && j.hkp <= kMaxPairs) {
       // Thread = (output column x, row group): the column's taps (up to four int16 pairs, two sets for Pillow's split 22-bit
       // taps) stay in registers; per row: the row's misalignment + the column's offset give an aligned word address and a funnel-
       // shift amount, three aligned words -> two shifts -> the eight tap bytes, one dp2a per tap pair.
@@ -398,6 +496,7 @@ struct AxisTable {
   std::vector<uint32_t> pairs;    // [out][kp * sets]: taps as int16 pairs (low half = even tap); 22-bit taps as hi set then lo set
   int ksize = 0, prec = 0, kp = 0, sets = 1;
   int max_rows = 0;               // input rows a 28-row output strip can touch
+  int hcols = 1;                  // adjacent outputs whose windows start within 4 inputs of each other: 4, 2 or 1 (pass1_multi)
 };
 
 static std::map<std::tuple<int, int, int>, AxisTable>& table_cache() {
@@ -419,6 +518,16 @@ static int get_table(int in_size, int out_size, int mode, const AxisTable** out)
     for (int y0 = 0; y0 + kStrip <= out_size; y0 += kStrip) {
       int last = y0 + kStrip - 1;
       t.max_rows = std::max(t.max_rows, t.bounds[2 * last] + t.bounds[2 * last + 1] - t.bounds[2 * y0]);
+    }
+    for (int nc : {4, 2}) {
+      if (out_size % nc) continue;
+      bool ok = true;
+      for (int o = 0; o < out_size && ok; o += nc) {
+        const int d = t.bounds[2 * (o + nc - 1)] - t.bounds[2 * o];
+        ok = d >= 0 && d <= 4;
+        for (int c = 1; c < nc && ok; ++c) ok = t.bounds[2 * (o + c)] >= t.bounds[2 * (o + c - 1)];
+      }
+      if (ok) { t.hcols = nc; break; }
     }
     // dp2a operands. ATen's taps are int16 already; Pillow's (22-bit precision) are split as c = hi * 2^11 + lo with
     // lo in [0, 2047]: sum(c * p) = (sum(hi * p) << 11) + sum(lo * p) exactly, and both halves fit int16.
@@ -511,7 +620,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
       const int ncols = ht[i] ? (int)(w * scale) + 2 * ht[i]->ksize + 8 : w;
       const int nvec = (15 + ncols * j.pix_stride + 15) >> 4;
       c.stage = nseg * rows_in * (nvec + 1) * 16;
-      c.planar = im.layout == KOCR_LAYOUT_HWC ? 3 * rows_in * ((ncols + 12 + 3) & ~3) + 16 : 0;
+      c.planar = im.layout == KOCR_LAYOUT_HWC ? 3 * rows_in * ((ncols + 20 + 3) & ~3) + 16 : 0;
       c.tab = 112 * 4 + (ht[i] ? w * ht[i]->kp * ht[i]->sets * 4 : 0);
       c.mid = planes * (rows_in + 1) * w + 16;
       c.res = vt[i] ? planes * kStrip * w : 0;
@@ -578,6 +687,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
       j.hb = reinterpret_cast<const int32_t*>(db + needs[ht[i]].off_b);
       j.hp = reinterpret_cast<const uint32_t*>(db + needs[ht[i]].off_p);
       j.hkp = ht[i]->kp; j.hsets = ht[i]->sets; j.hprec = ht[i]->prec;
+      j.hcols = ht[i]->hcols;
     }
     if (vt[i]) {
       j.vb = reinterpret_cast<const int32_t*>(db + needs[vt[i]].off_b);

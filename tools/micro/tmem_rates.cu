@@ -37,7 +37,7 @@ __global__ void k(long long* cyc_out, uint32_t* sink, int iters) {
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(base + (it & 1) * 32));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc ^= r[it & 31];
+      acc ^= r[0] ^ r[17] ^ r[31];
     } else if (MODE == 1) {
 #pragma unroll
       for (int c = 0; c < 2; ++c)
@@ -57,7 +57,7 @@ __global__ void k(long long* cyc_out, uint32_t* sink, int iters) {
             "=r"(r[74]), "=r"(r[75]), "=r"(r[76]), "=r"(r[77]), "=r"(r[78]), "=r"(r[79])
           : "r"(base + 64));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc ^= r[it % 80];
+      acc ^= r[0] ^ r[40] ^ r[79];
     } else {
 #pragma unroll
       for (int c = 0; c < 2; ++c)
@@ -71,7 +71,7 @@ __global__ void k(long long* cyc_out, uint32_t* sink, int iters) {
                    "r"(r[34]), "r"(r[35]), "r"(r[36]), "r"(r[37]), "r"(r[38]), "r"(r[39])
                    : "memory");
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      r[it & 31] += 1;
+      r[0] += 1; r[20] ^= r[0]; r[39] += r[20];
     }
   }
   const long long t1 = clock64();
