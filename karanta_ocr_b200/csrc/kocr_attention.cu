@@ -66,7 +66,7 @@ static constexpr int kPpAt = KOCR_PP_AT;  // the exponent phase is handed over a
 #endif
 static constexpr int kPolyEvery = KOCR_POLY_EVERY;  // every 4th pair of exponentials is evaluated on the FMA pipe instead of MUFU (0 = never)
 #ifndef KOCR_PROBE
-#define KOCR_PROBE 0   // timing probes (wrong results): bit 0 no exponentials, bit 1 no row max, bit 2 no TMEM score load, bit 3 no P store
+#define KOCR_PROBE 0   // timing probes (wrong results): bit 0 no exponentials, bit 1 no row max, bit 2 no TMEM score load, bit 3 no P store, bit 4 no row sum, bit 5 no subtraction, bit 6 no bf16 conversion
 #endif
 static constexpr int kProbe = KOCR_PROBE;
 static constexpr float kRescaleThreshold = 8.0f;
@@ -402,7 +402,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       uint32_t pk[kSub / 2];
 #pragma unroll
       for (int c = 0; c < kSub / 2; ++c) {
-        const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
+        const uint64_t x2 = (kProbe & 32) ? pack_u32x2(sr[2 * c], sr[2 * c + 1]) : add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
         uint64_t p2;
         if (kProbe & 1) {
           p2 = x2;
@@ -413,10 +413,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           unpack_f32x2(x2, x0, x1);
           p2 = pack_f32x2(ex2(x0), ex2(x1));
         }
-        acc2[c & 3] = add_f32x2(acc2[c & 3], p2);
+        if (!(kProbe & 16) || c < 4) acc2[c & 3] = add_f32x2(acc2[c & 3], p2);
         float p0, p1;
         unpack_f32x2(p2, p0, p1);
-        pk[c] = pack_bf16(p0, p1);
+        pk[c] = (kProbe & 64) ? (__float_as_uint(p0) ^ __float_as_uint(p1)) : pack_bf16(p0, p1);
         // hand the exponent phase to the other tile's warp once pair kPpAt is through the MUFU unit: the remaining
         // exponents cover the hand-over latency. The barrier id is made to depend on that pair's result (p >= 0, so the
         // sign bit adds nothing) because ptxas otherwise hoists the arrive to the top of the phase.

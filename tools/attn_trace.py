@@ -23,6 +23,8 @@ W, S, P = 12, 96, 12
 buf = np.zeros((W, S, P), dtype=np.int64)
 rc = lib.kocr_debug_attn_trace(C.c_void_p(buf.ctypes.data), C.c_int64(buf.nbytes))
 assert rc == 0, rc
+os.makedirs("gpurun_out", exist_ok=True)
+np.save("gpurun_out/attn_trace.npy", buf)
 lo, hi = 20, 70  # steady state
 names_s = ["wait s_full", "LDTM+wait::ld", "mask+row max", "token wait (bar.sync)", "exponents+sum", "STTM issue", "o_done wait", "rescale+wait::st", "fence+arrive", "loop back"]
 print("softmax warps: mean cycles per phase over sub-steps %d..%d" % (lo, hi))

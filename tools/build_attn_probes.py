@@ -5,13 +5,11 @@ from karanta_ocr_b200 import build
 VARIANTS = {
     "p1_noexp": ["KOCR_PROBE=1"],
     "p2_nomax": ["KOCR_PROBE=2"],
-    "p3_noexp_nomax": ["KOCR_PROBE=3"],
-    "p4_noldtm": ["KOCR_PROBE=4"],
-    "p8_nosttm": ["KOCR_PROBE=8"],
-    "p15_shell": ["KOCR_PROBE=15"],
-    "pp0": ["KOCR_PINGPONG=0"],
-    "poly0": ["KOCR_POLY_EVERY=0"],
-    "poly2": ["KOCR_POLY_EVERY=2"],
+    "p16_noacc": ["KOCR_PROBE=16"],
+    "p32_nosub": ["KOCR_PROBE=32"],
+    "p64_nocvt": ["KOCR_PROBE=64"],
+    "p114_noacc_nosub_nocvt_nomax": ["KOCR_PROBE=114"],
+    "p115_only_ldst": ["KOCR_PROBE=115"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
