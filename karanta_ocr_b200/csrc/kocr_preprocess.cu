@@ -53,6 +53,7 @@ struct TileInfo {
   int y0, x0, tw, r0, rows_in, xin0, ncols_in;
   int nseg, planes, Lp, nvec;   // staged segments (3 planar / 1), filtered planes (1 gray / 3), staged row pitch, vectors per row
   int lg_lpr;                   // log2 of the lanes that share one staged row in request_rows (>= nvec of them)
+  int ng, nrg, n_iter, magic;   // pass1_multi: column groups, row slices, iterations per thread, ceil(2^16 / ng) (tid / ng without a division)
   long long n0;                 // first token of the tile
 };
 
@@ -132,6 +133,12 @@ __device__ void plan_tile(const PageJob* __restrict__ jobs, int n_jobs, int tile
   t.nvec = (15 + t.ncols_in * j.pix_stride + 15) >> 4;
   t.Lp = (t.nvec + 1) * 16;
   t.lg_lpr = 32 - __clz(t.nvec - 1);  // nvec >= 2
+  if (j.hcols > 1 || !j.hb) {
+    t.ng = t.tw / (j.hb ? j.hcols : 4);
+    t.nrg = kThreads / t.ng;
+    t.magic = (65536 + t.ng - 1) / t.ng;
+    t.n_iter = (t.planes * t.rows_in + t.nrg - 1) / t.nrg;
+  }
   t.n0 = j.token_base + ((long long)sy * (j.out_w / kStrip) + t.x0 / kStrip) * 4;
 }
 
@@ -176,34 +183,51 @@ __device__ __forceinline__ void pass1_multi(const PageJob& j, const TileInfo& t,
                                             bool aligned_rows, const uint8_t* rowoff, const int32_t* xoff, const uint32_t* htab,
                                             uint8_t* mid, int mid_plane) {
   const int tw = t.tw, rows_in = t.rows_in, planes = t.planes, nseg = t.nseg;
-  const int ng = tw / NC;                            // column groups
-  const int nrg = kThreads / ng;                     // row slices side by side
-  const int g = threadIdx.x % ng, grp = threadIdx.x / ng;
+  const int ng = t.ng;                               // column groups
+  const int nrg = t.nrg;                             // row slices side by side
+  const int grp = (int)(((uint32_t)threadIdx.x * (uint32_t)t.magic) >> 16), g = (int)threadIdx.x - grp * ng;
   if (grp >= nrg) return;
-  const int hkp = j.hkp, hpw = hkp * j.hsets;
-  const bool four = hkp > 3;
-  const int xo0 = xoff[NC * g];
+  const bool four = j.hkp > 3;
+  // the tile's tap table is staged as [column][set][4 pairs] (zero padded): one 16-byte read per column and set
+  const int4 xo4 = NC == 4 ? *reinterpret_cast<const int4*>(xoff + 4 * g) : make_int4(xoff[2 * g], xoff[2 * g + 1], 0, 0);
+  const int xo0 = xo4.x;
+  const int xoc[4] = {xo4.x, xo4.y, xo4.z, xo4.w};
   uint32_t dsh[NC], k[NC][4], l[NC][4];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    dsh[c] = (uint32_t)(xoff[NC * g + c] - xo0) * 8u;   // 0, 8, ... 32
-    const uint32_t* kx = htab + (NC * g + c) * hpw;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      k[c][i] = i < hkp ? kx[i] : 0u;
-      l[c][i] = (kSplit && i < hkp) ? kx[hkp + i] : 0u;
+    dsh[c] = (uint32_t)(xoc[c] - xo0) * 8u;   // 0, 8, ... 32
+    const uint4* kx = reinterpret_cast<const uint4*>(htab) + (NC * g + c) * (kSplit ? 2 : 1);
+    const uint4 kk = kx[0];
+    k[c][0] = kk.x; k[c][1] = kk.y; k[c][2] = kk.z; k[c][3] = kk.w;
+    if (kSplit) {
+      const uint4 ll = kx[1];
+      l[c][0] = ll.x; l[c][1] = ll.y; l[c][2] = ll.z; l[c][3] = ll.w;
+    } else {
+      l[c][0] = l[c][1] = l[c][2] = l[c][3] = 0u;
     }
   }
   const int prec = j.hprec, round0 = 1 << (prec - 1);
   const int total = planes * rows_in;
+  // (plane, row) is walked as one flat index `it`: the staged segments follow each other (seg_rows == rows_in), so the row's
+  // address and its misalignment entry are linear in `it`; only the output plane pitch (rows_in + 1 rows) needs a wrap step
+  const int nseg3 = nseg == 3 || aligned_rows;
+  (void)nseg3;
+  (void)seg_rows;
+  uint32_t rp = smem_u32(rows_base) + (uint32_t)(grp * row_pitch_s);
+  const uint32_t rstep = (uint32_t)(nrg * row_pitch_s);
+  uint32_t rop = smem_u32(rowoff) + (uint32_t)grp;
+  int r = grp, plw = 0;
+  while (r >= rows_in) { r -= rows_in; ++plw; }
+  uint32_t mp = smem_u32(mid) + (uint32_t)(plw * mid_plane + r * tw + NC * g);
+  const uint32_t mstep = (uint32_t)(nrg * tw);
 #pragma unroll 2
   for (int it = grp; it < total; it += nrg) {
-    const int pl = (it >= rows_in) + (it >= 2 * rows_in), r = it - pl * rows_in;
-    const int srow = (aligned_rows ? pl : (nseg == 3 ? pl : 0)) * seg_rows + r;
-    const int boff = (aligned_rows ? 0 : (int)rowoff[(nseg == 3 ? pl : 0) * rows_in + r]) + xo0;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(rows_base + (size_t)srow * row_pitch_s + (boff & ~3));
-    const uint32_t sh = (uint32_t)(boff & 3) * 8u;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    uint32_t ro = 0;
+    if (!aligned_rows) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ro) : "r"(rop));
+    const uint32_t boff = ro + (uint32_t)xo0;
+    const uint32_t wa = rp + (boff & ~3u);
+    const uint32_t sh = (boff & 3u) * 8u;
+    const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4), w2 = lds_u32(wa + 8), w3 = lds_u32(wa + 12);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
     int o[NC];
 #pragma unroll
@@ -230,11 +254,55 @@ __device__ __forceinline__ void pass1_multi(const PageJob& j, const TileInfo& t,
       }
       o[c] = acc >> prec;
     }
-    uint8_t* mp = mid + pl * mid_plane + r * tw + NC * g;
     if (NC == 4) {
-      *reinterpret_cast<uint32_t*>(mp) = pack_sat_u8(o[1], o[0], pack_sat_u8(o[NC - 1], o[NC - 2], 0u));
+      const uint32_t v = pack_sat_u8(o[1], o[0], pack_sat_u8(o[NC - 1], o[NC - 2], 0u));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(mp), "r"(v) : "memory");
     } else {
-      *reinterpret_cast<uint16_t*>(mp) = (uint16_t)pack_sat_u8(o[1], o[0], 0u);
+      const uint32_t v = pack_sat_u8(o[1], o[0], 0u);
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(mp), "h"((unsigned short)v) : "memory");
+    }
+    rp += rstep;
+    rop += (uint32_t)nrg;
+    mp += mstep;
+    r += nrg;
+    while (r >= rows_in) {  // next plane of mid: its pitch is one row longer than the staged segment's
+      r -= rows_in;
+      mp += (uint32_t)tw;
+    }
+  }
+}
+
+// Width unchanged (no horizontal taps): the staged rows are re-aligned into mid, four pixels per thread and row - two aligned
+// words, one funnel shift, one store. Same flat (plane, row) walk as pass1_multi.
+__device__ __forceinline__ void pass1_copy(const TileInfo& t, const uint8_t* rows_base, int row_pitch_s, bool aligned_rows,
+                                           const uint8_t* rowoff, uint8_t* mid, int mid_plane) {
+  const int tw = t.tw, rows_in = t.rows_in;
+  const int ng = t.ng, nrg = t.nrg;
+  const int grp = (int)(((uint32_t)threadIdx.x * (uint32_t)t.magic) >> 16), g = (int)threadIdx.x - grp * ng;
+  if (grp >= nrg) return;
+  const int total = t.planes * rows_in;
+  uint32_t rp = smem_u32(rows_base) + (uint32_t)(grp * row_pitch_s);
+  const uint32_t rstep = (uint32_t)(nrg * row_pitch_s);
+  uint32_t rop = smem_u32(rowoff) + (uint32_t)grp;
+  int r = grp, plw = 0;
+  while (r >= rows_in) { r -= rows_in; ++plw; }
+  uint32_t mp = smem_u32(mid) + (uint32_t)(plw * mid_plane + r * tw + 4 * g);
+  const uint32_t mstep = (uint32_t)(nrg * tw);
+#pragma unroll 2
+  for (int it = grp; it < total; it += nrg) {
+    uint32_t ro = 0;
+    if (!aligned_rows) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ro) : "r"(rop));
+    const uint32_t boff = ro + 4u * (uint32_t)g;
+    const uint32_t wa = rp + (boff & ~3u);
+    const uint32_t v = __funnelshift_r(lds_u32(wa), lds_u32(wa + 4), (boff & 3u) * 8u);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(mp), "r"(v) : "memory");
+    rp += rstep;
+    rop += (uint32_t)nrg;
+    mp += mstep;
+    r += nrg;
+    while (r >= rows_in) {
+      r -= rows_in;
+      mp += (uint32_t)tw;
     }
   }
 }
@@ -245,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
                                                               void* __restrict__ out, int stage_bytes, int planar_off, int tab_off,
                                                               int mid_off, int res_off, int out_off) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ float lut[768];
+  __shared__ __align__(1024) float lut[768];  // 1 KB per channel: a table address is base | (byte << 2)
   __shared__ TileInfo tinfo[2];
   __shared__ uint8_t rowoff[2][3 * 256];
   for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
@@ -277,7 +345,15 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     uint32_t* htab = reinterpret_cast<uint32_t*>(smem + tab_off) + 112;    // [tw][hpw]
     if (j.hb) {
       for (int x = threadIdx.x; x < tw; x += kThreads) xoff[x] = j.hb[2 * (t.x0 + x)] - t.xin0;
-      for (int i = threadIdx.x; i < tw * hpw; i += kThreads) htab[i] = j.hp[(size_t)t.x0 * hpw + i];
+      if (j.hcols > 1) {  // pass1_multi: [column][set][4] with zero padding
+        const int hkp = j.hkp, lg_per = j.hsets == 2 ? 3 : 2, per = 1 << lg_per;
+        for (int i = threadIdx.x; i < tw * per; i += kThreads) {
+          const int x = i >> lg_per, e = i & (per - 1), st = e >> 2, kk = e & 3;
+          htab[i] = kk < hkp ? j.hp[(size_t)(t.x0 + x) * hpw + st * hkp + kk] : 0u;
+        }
+      } else {
+        for (int i = threadIdx.x; i < tw * hpw; i += kThreads) htab[i] = j.hp[(size_t)t.x0 * hpw + i];
+      }
     }
     cp_async_wait<0>();  // this tile's rows have landed
     __syncthreads();
@@ -310,7 +386,9 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
     // share their misalignment modulo 4 when walked with a constant pitch, so the word offset and the funnel-shift amount of
     // the column's tap window are loop constants; per row: three aligned words, two funnel shifts, one dp2a per tap pair.
     const int nseg = t.nseg;
-    if (j.hb && j.hkp <= kMaxPairs && j.hcols > 1) {
+    if (!j.hb) {
+      pass1_copy(t, rows_base, row_pitch_s, aligned_rows, rowoff[buf], mid, mid_plane);
+    } else if (j.hkp <= kMaxPairs && j.hcols > 1) {
       const uint8_t* ro = rowoff[buf];
       if (j.hcols == 4) {
         if (j.hsets == 2) pass1_multi<4, true>(j, t, rows_base, row_pitch_s, seg_rows, aligned_rows, ro, xoff, htab, mid, mid_plane);
@@ -458,12 +536,17 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(const PageJob* 
       const int cell = rem / kStrip, y = rem - cell * kStrip;
       const int mh = y >= 14 ? 1 : 0, py = y - 14 * mh;
       const uint32_t* p = reinterpret_cast<const uint32_t*>(res + (planes == 1 ? 0 : c) * res_plane + y * tw + cell * kStrip);
-      const float* l = lut + c * 256;
+      const uint32_t lb = smem_u32(lut) + (uint32_t)c * 1024u;
+      auto lut_at = [lb](uint32_t idx4) {  // idx4 = byte << 2 (already masked)
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(lb | idx4));
+        return v;
+      };
       uint8_t* d0 = obuf + ((size_t)(cell * 4 + mh * 2) * kPatchDim + c * 392 + py * 14) * kElt;  // token mw = 0; mw = 1 is kPatchDim further
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         const uint32_t u = p[k];
-        const float v0 = l[u & 255], v1 = l[(u >> 8) & 255], v2 = l[(u >> 16) & 255], v3 = l[u >> 24];
+        const float v0 = lut_at((u << 2) & 0x3fcu), v1 = lut_at((u >> 6) & 0x3fcu), v2 = lut_at((u >> 14) & 0x3fcu), v3 = lut_at((u >> 22) & 0x3fcu);
         // pixels 4k..4k+3 of the 28: pixel pairs never straddle the two tokens (14 is even)
         const int pa = 4 * k, pb = 4 * k + 2;
         uint8_t* da = d0 + ((pa >= 14 ? kPatchDim - 14 : 0) + pa) * kElt;
@@ -621,7 +704,7 @@ extern "C" int kocr_preprocess(KocrCtx* ctx_, const KocrImage* images, int n_ima
       const int nvec = (15 + ncols * j.pix_stride + 15) >> 4;
       c.stage = nseg * rows_in * (nvec + 1) * 16;
       c.planar = im.layout == KOCR_LAYOUT_HWC ? 3 * rows_in * ((ncols + 20 + 3) & ~3) + 16 : 0;
-      c.tab = 112 * 4 + (ht[i] ? w * ht[i]->kp * ht[i]->sets * 4 : 0);
+      c.tab = 112 * 4 + (ht[i] ? w * std::max(ht[i]->kp, 4) * ht[i]->sets * 4 : 0);
       c.mid = planes * (rows_in + 1) * w + 16;
       c.res = vt[i] ? planes * kStrip * w : 0;
       c.outb = (w / kStrip) * 4 * kPatchDim * elt;
