@@ -320,7 +320,7 @@ def run_gpu(args):
                                  "seconds": ms_j / 1e3, "pages_per_rank": n_mine,
                                  "what": "one job of job_pages letter pages sharded over the ranks (LPT, no collective), 64-page batches, "
                                          "pinned host pages in -> host embeddings out; 8192 pages at N > 1, 1024 at N = 1"}
-        png_pages = 256 * world
+        png_pages = 512 * world
         ms_p, _, _, h2d_p = bulk_job(enc, vars(cfg), world, rank, dev, png_pages, 1, 1, png=True)
         extras["e2e_from_png"] = {"value": png_pages / (ms_p / 1e3), "unit": UNIT, "job_pages": png_pages, "h2d_bytes_per_rank": h2d_p,
                                   "what": "same job with the pages given as RGB PNG files: inflate + scan-line filters on the GPU inside the "

@@ -99,6 +99,10 @@ KOCR_API int kocr_window_index(const int64_t* grid_thw, int n_images, int window
  * device is absent or is not compute capability 10.x: there is no CPU fallback. */
 KOCR_API int kocr_create(int device, KocrCtx** out);
 KOCR_API void kocr_destroy(KocrCtx* ctx);
+/* Keep `n` SMs (0 <= n <= half the device) out of the tower's persistent GEMM grids and let kocr_png_decode use at most
+ * that many: page decode for the NEXT batch then runs beside the tower of the current one (a side stream of higher
+ * priority) instead of stealing SMs from one-CTA-per-SM kernels that were sized for the whole device.  0 (default) = off. */
+KOCR_API int kocr_set_reserved_sms(KocrCtx* ctx, int n);
 
 /* ------------------------------------------------------------------ image processor (device) */
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     "kocr_window_index": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "kocr_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "kocr_destroy": (None, [C.c_void_p]),
+    "kocr_set_reserved_sms": (C.c_int, [C.c_void_p, C.c_int]),
     "kocr_preprocess": (C.c_int, [C.c_void_p, C.POINTER(KocrImage), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "kocr_tower_create": (C.c_int, [C.c_void_p, C.POINTER(KocrTowerConfig), C.POINTER(C.c_void_p)]),

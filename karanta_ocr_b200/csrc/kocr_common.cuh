@@ -55,6 +55,7 @@ struct Ctx {
   int device = 0;
   float* d_lut[2] = {nullptr, nullptr};  // normalise LUT per resize mode, [3][256] f32
   int num_sms = 148;
+  int reserved_sms = 0;  // SMs left to the page-decode kernels (kocr_set_reserved_sms); persistent GEMM grids exclude them
   int cc_major = 0, cc_minor = 0;
   // pinned staging ring for small per-call tables (H2D without a device sync)
   static constexpr int kSlots = 8;

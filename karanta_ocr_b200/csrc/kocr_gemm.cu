@@ -421,7 +421,7 @@ static int launch_one(Ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, co
   auto kern = gemm_kernel<BN, EPI>;
   if (int rc = ctx->opt_in_smem(reinterpret_cast<const void*>(kern), S::kTotal)) return rc;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = std::min(tiles, ctx->num_sms);
+  const int grid = std::min(tiles, ctx->num_sms - ctx->reserved_sms);  // one persistent CTA per SM that is ours
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, ep, M, N, K);
   KOCR_LAUNCH_CHECK("gemm_kernel");
   return KOCR_OK;

@@ -458,6 +458,13 @@ int kocr_create(int device, KocrCtx** out) {
   return KOCR_OK;
 }
 
+int kocr_set_reserved_sms(KocrCtx* ctx_, int n) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || n < 0 || n > ctx->num_sms / 2) return fail(KOCR_ERR_INVALID, "kocr_set_reserved_sms: n must be in [0, SMs / 2]");
+  ctx->reserved_sms = n;
+  return KOCR_OK;
+}
+
 void kocr_destroy(KocrCtx* ctx) {
   if (!ctx) return;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -13,6 +13,8 @@
 // under the previous batch's tower.
 #include <string.h>
 
+#include <algorithm>
+
 #include <vector>
 
 #include "kocr_common.cuh"
@@ -33,8 +35,7 @@ static constexpr int kPngWarps = 8;  // pages per CTA: few CTAs, so that a decod
 __global__ void __launch_bounds__(kPngWarps * 32) inflate_kernel(const PngJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status) {
   __shared__ inflate::Tables tabs[kPngWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.x * kPngWarps + warp;
-  if (job >= n_jobs) return;
+  for (int job = blockIdx.x * kPngWarps + warp; job < n_jobs; job += gridDim.x * kPngWarps) {  // the grid may be capped (reserved SMs)
   const PngJob j = jobs[job];
   inflate::Tables& t = tabs[warp];
   inflate::State s;
@@ -82,6 +83,8 @@ __global__ void __launch_bounds__(kPngWarps * 32) inflate_kernel(const PngJob* _
     }
   }
   if (lane == 0) status[job] = s.status;
+  __syncwarp();
+  }
 }
 
 // Scan-line reconstruction in place in `raw`, pixels (alpha dropped) to `out`. Lane k of the warp owns row r0 + k of a
@@ -90,10 +93,9 @@ __global__ void __launch_bounds__(kPngWarps * 32) inflate_kernel(const PngJob* _
 // (the previous band finished it). A pixel is up to 4 bytes, carried packed in one register.
 __global__ void __launch_bounds__(kPngWarps * 32) unfilter_kernel(const PngJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.x * kPngWarps + warp;
-  if (job >= n_jobs) return;
+  for (int job = blockIdx.x * kPngWarps + warp; job < n_jobs; job += gridDim.x * kPngWarps) {
   const PngJob j = jobs[job];
-  if (status[job] != 0) return;  // inflate failed: nothing to reconstruct
+  if (status[job] != 0) continue;  // inflate failed: nothing to reconstruct
   const long long pitch = 1 + (long long)j.width * j.bpp;
   int bad = 0;
   for (int r0 = 0; r0 < j.height; r0 += 32) {
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kPngWarps * 32) unfilter_kernel(const PngJob* 
   }
   bad = __any_sync(0xffffffffu, bad);
   if (lane == 0 && bad) status[job] = inflate::kErrFilter;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host: container parsing
@@ -307,7 +310,8 @@ int kocr_png_decode(KocrCtx* ctx_, const uint8_t* const* files, const int64_t* s
   if (rc) return rc;
   StageGuard guard(ctx, slot, stream);
   ProfScope ps(ctx, kProfOther, stream);
-  const int grid = (n + kPngWarps - 1) / kPngWarps;
+  int grid = (n + kPngWarps - 1) / kPngWarps;
+  if (ctx->reserved_sms > 0) grid = std::min(grid, ctx->reserved_sms);  // the tower's persistent grids leave exactly these SMs free
   inflate_kernel<<<grid, kPngWarps * 32, 0, stream>>>(static_cast<const PngJob*>(d_jobs), n, status_dev);
   KOCR_LAUNCH_CHECK("inflate_kernel");
   unfilter_kernel<<<grid, kPngWarps * 32, 0, stream>>>(static_cast<const PngJob*>(d_jobs), n, status_dev);

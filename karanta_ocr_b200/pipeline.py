@@ -90,6 +90,7 @@ class PageEncoder:
         return outs, mine
 
     accepts_png_bytes = True  # pages may be undecoded PNG files (bytes / data URIs): they are decoded on the GPU
+    decode_sms = 8            # SMs given to the decode kernels while PNG pages stream through encode_to_host_async
 
     def _decode_png_entries(self, pages, check: bool):
         """Replace the entries of `pages` that are PNG files (bytes, or base64 / data-URI strings as the reference's requests
@@ -130,7 +131,14 @@ class PageEncoder:
         kernels on the input stream as well; after the event `last_png_status` = (their indices, int32 status tensor, 0 = ok)."""
         dev = self.tower.device
         if not hasattr(self, "_s_in"):
-            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            # the input stream outranks the tower's: when an SM frees up, a waiting decode / preprocess CTA goes first
+            self._s_in, self._s_out = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)
+        if not getattr(self, "_reserved", False) and any(isinstance(p, (bytes, bytearray, memoryview, str)) for p in pages):
+            # undecoded pages: their decode runs beside the previous batch's tower on a few SMs that the tower's persistent
+            # GEMM grids leave alone from now on (csrc: kocr_set_reserved_sms)
+            from . import _lib
+            _lib.check(_lib.load().kocr_set_reserved_sms(_lib.context(dev.index if dev.index is not None else torch.cuda.current_device()), self.decode_sms))
+            self._reserved = True
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(self._s_in):
             # undecoded PNG files: inflate + unfilter on the input stream too, under the previous batch's tower
