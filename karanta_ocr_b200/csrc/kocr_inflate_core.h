@@ -34,7 +34,7 @@ enum Status : int32_t {
 };
 
 // What lane 0 hands to the warp when it stops decoding.
-enum Event : int32_t { kEvMatch = 0, kEvRefill = 1, kEvDone = 2, kEvError = 3 };
+enum Event : int32_t { kEvMatch = 0, kEvRefill = 1, kEvDone = 2, kEvError = 3, kEvFlush = 4 };
 
 struct Tables {            // per stream, in shared memory on the device
   uint16_t lit_fast[1 << kLitFastBits];   // (symbol << 4) | code length, 0 = longer than the fast width (or unused)
@@ -42,7 +42,7 @@ struct Tables {            // per stream, in shared memory on the device
   uint16_t lit_count[kMaxBits + 1], dist_count[kMaxBits + 1];  // canonical code: codes per length
   uint16_t lit_symbol[288], dist_symbol[32];                   // symbols ordered by code
   uint8_t lengths[320];                                        // scratch while a dynamic header is read
-  uint8_t window[kWindow];                                     // compressed bytes [base, base + kWindow)
+  alignas(16) uint8_t window[kWindow];                         // compressed bytes [base, base + kWindow), read as aligned 32-bit words
 };
 
 struct State {
@@ -53,6 +53,10 @@ struct State {
   int64_t win_base = 0;     // window holds input bytes [win_base, win_base + kWindow)
   int64_t out_pos = 0;
   int64_t out_size = 0;
+  // `out` may be a ring (the device keeps the last 32 KB of output in shared memory and streams it to HBM behind the decoder):
+  // bytes go to out[out_pos & out_mask], and run() yields kEvFlush once out_pos reaches flush_at. A plain buffer: mask -1.
+  int64_t out_mask = -1;
+  int64_t flush_at = INT64_MAX;
   int phase = 0;            // 0 = zlib header, 1 = block header, 2 = stored block, 3 = Huffman block, 4 = finished
   int last_block = 0;
   int stored_left = 0;
@@ -79,14 +83,17 @@ __device__ static const uint8_t kClOrder_d[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10,
 #define KOCR_TAB(name) name
 #endif
 
-// ---- bit reader over the window (LSB first, RFC 1951 section 3.1.1). Bytes past the end of the input read as zero; running
-// past the end is detected by the caller through in_pos.
+// ---- bit reader over the window (LSB first, RFC 1951 section 3.1.1). The buffer is topped up four bytes at a time with one
+// aligned word read (in_pos stays a multiple of 4), which leaves at least 32 valid bits behind every call - enough for any one
+// step below (a literal/length code with its extra bits is at most 20 bits, a distance code with extra bits 28, a stored
+// block's LEN/NLEN 32). Bytes past the end of the input read as zero (the window is zero-filled there); running past the end
+// is detected by the caller through in_pos.
 KOCR_HD void refill_bits(State& s, const Tables& t) {
-  while (s.bitcnt <= 56) {
-    const uint64_t b = s.in_pos < s.in_size ? t.window[s.in_pos & (kWindow - 1)] : 0;
-    s.bitbuf |= b << s.bitcnt;
-    s.bitcnt += 8;
-    ++s.in_pos;
+  if (s.bitcnt <= 32) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&t.window[s.in_pos & (kWindow - 1)]);
+    s.bitbuf |= (uint64_t)w << s.bitcnt;
+    s.bitcnt += 32;
+    s.in_pos += 4;
   }
 }
 KOCR_HD uint32_t peek(const State& s, int n) { return (uint32_t)(s.bitbuf & ((1ull << n) - 1)); }
@@ -228,6 +235,7 @@ KOCR_HD int run(State& s, Tables& t, uint8_t* out) {
       return kEvError;
     }
     if (s.in_pos >= s.win_base + kHalf && s.win_base + kWindow < s.in_size && s.phase != 4) return kEvRefill;
+    if (s.out_pos >= s.flush_at) return kEvFlush;
     refill_bits(s, t);
     switch (s.phase) {
       case 0: {  // zlib header (RFC 1950): CM = 8, window <= 32K, no preset dictionary, header checksum
@@ -271,28 +279,36 @@ KOCR_HD int run(State& s, Tables& t, uint8_t* out) {
         break;
       }
       case 2: {  // stored bytes, a few per round so that the refill check above stays in charge
-        int n = s.stored_left < 6 ? s.stored_left : 6;
+        int n = s.stored_left < 4 ? s.stored_left : 4;
         if (s.out_pos + n > s.out_size) {
           s.status = kErrOverflow;
           return kEvError;
         }
         s.stored_left -= n;
-        while (n--) out[s.out_pos++] = (uint8_t)take(s, 8);
+        while (n--) out[s.out_pos++ & s.out_mask] = (uint8_t)take(s, 8);
         if (s.stored_left == 0) s.phase = s.last_block ? 4 : 1;
         break;
       }
       case 3: {
-        const int sym = decode_symbol(s, t.lit_fast, kLitFastBits, t.lit_count, t.lit_symbol);
+        // literals are taken in a short inner loop (up to 8 symbols, < 50 input bytes: far inside the window's look-ahead) so
+        // that the checks at the top of the outer loop are paid once per round, not once per byte
+        int sym = 0;
+        for (int k = 0; k < 8; ++k) {
+          if (k) refill_bits(s, t);
+          sym = decode_symbol(s, t.lit_fast, kLitFastBits, t.lit_count, t.lit_symbol);
+          if (sym < 0 || sym >= 256) break;
+          if (s.out_pos >= s.out_size) {
+            s.status = kErrOverflow;
+            return kEvError;
+          }
+          out[s.out_pos++ & s.out_mask] = (uint8_t)sym;
+        }
         if (sym < 0) {
           s.status = kErrCode;
           return kEvError;
         }
         if (sym < 256) {
-          if (s.out_pos >= s.out_size) {
-            s.status = kErrOverflow;
-            return kEvError;
-          }
-          out[s.out_pos++] = (uint8_t)sym;
+          // eight literals: next round
         } else if (sym == 256) {
           s.phase = s.last_block ? 4 : 1;
         } else {
