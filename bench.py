@@ -297,7 +297,7 @@ def run_gpu(args):
         sampler.start()
     lib.kocr_profile_begin(ctx)
     ms = timed(step_resident, args.steps)
-    ncls = 10
+    ncls = 16  # the library reports as many classes as it has (names past the last one are empty)
     cls_ms = (C.c_double * ncls)()
     cls_n = (C.c_int64 * ncls)()
     lib.kocr_profile_end(ctx, ncls, cls_ms, cls_n)
@@ -332,17 +332,26 @@ def run_gpu(args):
         e2e = world * n_pages * args.steps / (ms_e2e / 1e3)
         names = [lib.kocr_profile_class_name(i).decode() for i in range(ncls)]
         per_class = {names[i]: {"ms_per_launch": cls_ms[i] / max(cls_n[i], 1), "launches": int(cls_n[i]), "ms_total": cls_ms[i]}
-                     for i in range(ncls) if cls_n[i]}
+                     for i in range(ncls) if cls_n[i] and names[i]}
         dom = max(per_class, key=lambda k: per_class[k]["ms_total"])
         D, F = cfg.embed_dim, cfg.mlp_hidden
         fc1_mult = 2.0 if cfg.arch == "qwen2_5_vl" else 1.0  # gate and up projections
         flops_by_class = {"attention": flops_attn_launch, "gemm_qkv_rope": 2.0 * N * D * 3 * D, "gemm_proj": 2.0 * N * D * D,
                           "gemm_fc1": 2.0 * N * D * F * fc1_mult, "gemm_fc2": 2.0 * N * D * F, "gemm_patch_embed": 2.0 * N * 1176 * D}
+        if cfg.arch == "qwen2_5_vl":  # full-attention layers only: the windowed ones are a different kernel shape with its own class
+            n_full = len(cfg.fullatt_block_indexes)
+            flops_by_class["attention"] = sum(fl["attention_per_layer"][i] for i in cfg.fullatt_block_indexes) / max(n_full, 1)
         for k, v in per_class.items():
             if k in flops_by_class:
                 v["tflops"] = flops_by_class[k] / (v["ms_per_launch"] * 1e-3) / 1e12
+        if "attention_windowed" in per_class:  # HBM-bound shape: qkv in (3 S D bf16) + output (S D bf16), ~0.13 TFLOP per layer
+            v = per_class["attention_windowed"]
+            v["bytes_per_launch"] = 4 * N * D * 2
+            v["gbs"] = v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9
+            v["frac_of_hbm"] = v["gbs"] / pk["hbm_gbs"]
+            v["bound"] = "hbm"
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp) and n_pages == PAGES_PER_STEP and args.workload == "c2":  # ncu dram__bytes_read+write per launch at this batch size
             tj = json.load(open(tp))
             traffic, traffic_src = tj["dram_bytes_per_launch"].get(dom), tj["source"]

@@ -92,7 +92,7 @@ struct Ctx {
 };
 
 enum ProfClass { kProfPreprocess = 0, kProfPatchEmbed, kProfNorm, kProfQkvRope, kProfAttention, kProfProj, kProfFc1, kProfFc2,
-                 kProfMerger, kProfOther, kProfClasses };
+                 kProfMerger, kProfOther, kProfAttentionWin, kProfClasses };
 
 // Releases a staging slot at scope exit (after the consumers were enqueued, or on an early error return).
 struct StageGuard {

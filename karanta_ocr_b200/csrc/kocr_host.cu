@@ -338,7 +338,7 @@ cudaEvent_t Ctx::prof_event() {
 }
 
 static const char* kProfNames[kProfClasses] = {"preprocess", "gemm_patch_embed", "norm", "gemm_qkv_rope", "attention",
-                                               "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_merger", "other"};
+                                               "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_merger", "other", "attention_windowed"};
 
 }  // namespace kocr
 

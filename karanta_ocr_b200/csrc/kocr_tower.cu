@@ -562,7 +562,7 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
       if ((rc = launch_gemm(ctx, x, D, b.w_qkv, D, S, 3 * D, D, kEpiQkvRope, e1, st))) return rc;
     }
     {
-      ProfScope ps(ctx, kProfAttention, st);
+      ProfScope ps(ctx, full ? kProfAttention : kProfAttentionWin, st);
       if (full) rc = launch_attention(ctx, qkv, attn, d_wf, n_work_full, H, S, st);
       else rc = launch_attention(ctx, qkv, attn, d_ww, n_work_win, H, S, st, d_rw);
       if (rc) return rc;

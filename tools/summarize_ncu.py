@@ -1,6 +1,6 @@
 """Turn the ncu outputs of tools/gpu_final.sh into the tracked summaries under profiles/:
-  launches csv (gpu__time_duration per launch of the bench command)  -> r1_ncu_launch_summary_bench_pages8.csv
-  full report (.ncu-rep, one prof_target.py run at the C2 batch size) -> r1_ncu_full_kernels_pages64.csv, r1_traffic.json
+  launches csv (gpu__time_duration per launch of the bench command)  -> r2_ncu_launch_summary_bench_pages8.csv
+  full report (.ncu-rep, one prof_target.py run at the C2 batch size) -> r2_ncu_full_kernels_pages64.csv, r2_traffic.json
 Usage: python tools/summarize_ncu.py gpurun_out/launches_final.csv gpurun_out/prof_final_raw.csv   (or the .ncu-rep)"""
 import csv
 import io
@@ -63,7 +63,7 @@ def launch_summary(path):
         a[0] += 1
         a[1] += v_ms
     total = sum(a[1] for a in agg.values())
-    out = os.path.join(PROF, "r1_ncu_launch_summary_bench_pages8.csv")
+    out = os.path.join(PROF, "r2_ncu_launch_summary_bench_pages8.csv")
     with open(out, "w") as f:
         f.write("kernel,launches,total_ms,share_pct,avg_us\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -88,7 +88,7 @@ def full_summary(rep):
         cls = classify(r[ci["Kernel Name"]], seen)
         if cls:
             last[cls] = r
-    out = os.path.join(PROF, "r1_ncu_full_kernels_pages64.csv")
+    out = os.path.join(PROF, "r2_ncu_full_kernels_pages64.csv")
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["class", "Kernel Name", "Grid Size", "Block Size"] + [f"{c} [{units[ci[c]]}]" for c in COLS])
@@ -104,10 +104,10 @@ def full_summary(rep):
         v, u = float(r[ci["gpu__time_duration.sum"]].replace(",", "")), units[ci["gpu__time_duration.sum"]].lower()
         return v * {"ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}[u]
     tj = {"source": "ncu --set full --clock-control none, tools/prof_target.py 64 (C2 batch: 64 letter pages, Qwen2-VL-7B widths, depth 1), "
-                    "warm launch of each kernel; profiles/r1_ncu_full_kernels_pages64.csv",
+                    "warm launch of each kernel; profiles/r2_ncu_full_kernels_pages64.csv",
           "dram_bytes_per_launch": {k: int(to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) for k, r in last.items()},
           "ncu_ms_per_launch": {k: to_ms(r) for k, r in last.items()}}
-    out = os.path.join(PROF, "r1_traffic.json")
+    out = os.path.join(PROF, "r2_traffic.json")
     json.dump(tj, open(out, "w"), indent=1)
     print("wrote", out)
     for k, r in last.items():
