@@ -39,6 +39,7 @@ struct Plan {
   cudaEvent_t used = nullptr;       // recorded after the last forward that reads the tables was enqueued
   cudaStream_t last_stream = nullptr;
   bool multi_stream = false;
+  bool pinned = false;              // a captured CUDA graph reads the tables: never evicted or rebuilt
   uint64_t tick = 0;
 };
 
@@ -195,7 +196,10 @@ static int get_plan(Tower* t, const int64_t* grid_thw, int n_images, cudaStream_
     KOCR_CUDA_CHECK(cudaEventCreateWithFlags(&p->used, cudaEventDisableTiming));
     t->plans.push_back(p);
   } else {
-    p = *std::min_element(t->plans.begin(), t->plans.end(), [](const Plan* a, const Plan* b) { return a->tick < b->tick; });
+    p = nullptr;
+    for (Plan* q : t->plans)
+      if (!q->pinned && (!p || q->tick < p->tick)) p = q;
+    if (!p) return fail(KOCR_ERR_STATE, "kocr_tower_forward: every cached plan belongs to a captured CUDA graph; destroy the tower to release them");
     if (p->multi_stream) KOCR_CUDA_CHECK(cudaDeviceSynchronize());
     else KOCR_CUDA_CHECK(cudaEventSynchronize(p->used));  // ~16 forwards old: normally long complete
   }
@@ -476,17 +480,32 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
 
   // ---- plan: positions, sequences, windows (cached per grid_thw)
   KOCR_CUDA_CHECK(cudaSetDevice(ctx->device));
+  // Under stream capture (CUDA graphs: call the forward once eagerly with this grid_thw first, so that the plan exists and the
+  // one-time attribute / table work is done) no event may tie the capture to work outside it: the plan is pinned instead.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  KOCR_CUDA_CHECK(cudaStreamIsCapturing(st, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   Plan* plan = nullptr;
-  if ((rc = get_plan(t, grid_thw, n_images, st, &plan))) return rc;
-  if (plan->last_stream != st) {  // built or last used on another stream: order this stream after it
-    KOCR_CUDA_CHECK(cudaStreamWaitEvent(st, plan->used, 0));
-    plan->multi_stream = true;
-    plan->last_stream = st;
+  if (capturing) {
+    std::lock_guard<std::mutex> lk(t->plan_mu);
+    const size_t nk = (size_t)n_images * 3;
+    for (Plan* p : t->plans)
+      if (p->key.size() == nk && memcmp(p->key.data(), grid_thw, nk * sizeof(int64_t)) == 0) plan = p;
+    if (!plan) return fail(KOCR_ERR_STATE, "kocr_tower_forward: capture needs a cached plan - run one eager forward with this grid_thw first");
+    if (plan->max_pos > t->rope_max_pos) return fail(KOCR_ERR_STATE, "kocr_tower_forward: capture needs the rotary table in place - run one eager forward first");
+    plan->pinned = true;
+  } else {
+    if ((rc = get_plan(t, grid_thw, n_images, st, &plan))) return rc;
+    if (plan->last_stream != st) {  // built or last used on another stream: order this stream after it
+      KOCR_CUDA_CHECK(cudaStreamWaitEvent(st, plan->used, 0));
+      plan->multi_stream = true;
+      plan->last_stream = st;
+    }
   }
   struct PlanUse {  // the tables stay alive (not evicted / overwritten) until every forward that reads them has run
-    Plan* p; cudaStream_t s;
-    ~PlanUse() { cudaEventRecord(p->used, s); }
-  } plan_use{plan, st};
+    Plan* p; cudaStream_t s; bool on;
+    ~PlanUse() { if (on) cudaEventRecord(p->used, s); }
+  } plan_use{plan, st, !capturing};
   const int S = plan->S, max_pos = plan->max_pos;
   const WsLayout wl = ws_layout(*t, S, pv_dtype == KOCR_DTYPE_F32);
   if ((int64_t)wl.total > workspace_bytes) return fail(KOCR_ERR_INVALID, "kocr_tower_forward: workspace too small");

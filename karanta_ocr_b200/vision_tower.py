@@ -57,6 +57,19 @@ def normalize_config(config) -> dict:
 _DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
 
 
+class GraphedForward:
+    """A captured tower forward (KarantaVisionTower.capture): copy the page's pixel_values into `.pixel_values`, call replay()."""
+
+    def __init__(self, graph, pixel_values, output, grid_thw):
+        self.graph, self.pixel_values, self.output, self.grid_thw = graph, pixel_values, output, grid_thw
+
+    def replay(self, pixel_values=None):
+        if pixel_values is not None:
+            self.pixel_values.copy_(pixel_values.reshape(self.pixel_values.shape), non_blocking=True)
+        self.graph.replay()
+        return self.output
+
+
 class KarantaVisionTower(torch.nn.Module):
     def __init__(self, config, device=None, hf_output: bool = False):
         super().__init__()
@@ -182,13 +195,36 @@ class KarantaVisionTower(torch.nn.Module):
                                                 self._ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(rc)
             self.last_launch_count = int(_lib.load().kocr_last_launch_count())
-            x.record_stream(torch.cuda.current_stream(dev))
+            if not torch.cuda.is_current_stream_capturing():
+                x.record_stream(torch.cuda.current_stream(dev))
         if self.hf_output:
             from transformers.modeling_outputs import BaseModelOutputWithPooling
             return BaseModelOutputWithPooling(last_hidden_state=hid, pooler_output=out)
         if return_hidden:
             return out, hid
         return out
+
+    @torch.no_grad()
+    def capture(self, grid_thw, dtype=torch.bfloat16):
+        """CUDA-graph form of forward() for one grid_thw (a serving loop sees the same page shape again and again): returns
+        a GraphedForward whose `.pixel_values` [sum N, 1176] is the static input and whose `replay()` launches the whole
+        tower as one graph and returns the static output tensor. One eager forward is run first (plan, rotary table and
+        shared-memory opt-ins must exist before the capture); the tables of that plan stay pinned for the tower's lifetime."""
+        g = np.ascontiguousarray(np.asarray(grid_thw.cpu() if isinstance(grid_thw, torch.Tensor) else grid_thw, dtype=np.int64).reshape(-1, 3))
+        S = int((g[:, 0] * g[:, 1] * g[:, 2]).sum())
+        patch_dim = self.cfg["in_channels"] * self.cfg["temporal_patch_size"] * self.cfg["patch_size"] ** 2
+        dev = self._device
+        with torch.cuda.device(dev):
+            pv = torch.zeros((S, patch_dim), dtype=dtype, device=dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.forward(pv, g)  # warm-up outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward(pv, g)
+        return GraphedForward(graph, pv, out, g)
 
     @classmethod
     def replace_visual(cls, model, device=None):
