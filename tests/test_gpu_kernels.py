@@ -153,3 +153,24 @@ def test_attention_longest_sequence():
     out2 = gu.op_attention(gu.pack_qkv(q, kc, v), [0, S], H).float().reshape(S, H, 80)
     mean_v = v.float().mean(0, keepdim=True).expand(S, H, 80)
     assert ((out2 - mean_v).abs().max() / mean_v.abs().max()).item() <= 2e-2
+
+
+@pytest.mark.parametrize("gain", [6.0, 40.0, 400.0, 2000.0])
+def test_attention_scores_that_keep_growing(gain):
+    """The softmax reference is only moved when a score outgrows it (the common sub-step takes no row maximum at all and
+    notices growth from the exponent bits of P): keys whose scores climb along the sequence - by a little per sub-step, by
+    more than 2^9 per sub-step, and by more than the f32 exponent range per sub-step - force the redo path again and again,
+    for some rows only (the query sign flips per row), and the last key block must dominate exactly as in the reference."""
+    S, H = 1000, 2
+    g = torch.Generator().manual_seed(5)
+    q = torch.zeros(S, H, 80)
+    q[:, :, 0] = torch.where(torch.arange(S) % 3 == 0, -1.0, 1.0)[:, None] * (80 ** 0.5) / 1.4426950408889634  # score = +-k[.,0] in log2 units
+    q[:, :, 1:] = torch.randn(S, H, 79, generator=g) * 0.05
+    k = torch.randn(S, H, 80, generator=g) * 0.05
+    k[:, :, 0] = (torch.arange(S) // 80).float()[:, None] * gain / 12.0 + torch.randn(S, H, generator=g) * 0.3   # climbs by `gain / 12` per 80-key tile
+    v = torch.randn(S, H, 80, generator=g)
+    q, k, v = (t.to(torch.bfloat16).cuda() for t in (q, k, v))
+    out = gu.op_attention(gu.pack_qkv(q, k, v), [0, S], H)
+    ref = gu.attention_reference(q, k, v, [0, S]).reshape(S, H * 80)
+    assert torch.isfinite(out.float()).all()
+    _close(out, ref, 2e-2)
