@@ -21,7 +21,11 @@
 // 80 exponentials, pack, TMEM store, barrier round trips); the two tiles' warps take turns on the MUFU unit (kPingPong).
 // TMEM: S[t][b] at t*160 + b*80 (80 columns); P[t][b] (bf16) overwrites the first 40 columns of S[t][b]; O_t at 320 + t*80
 // (windowed shape: 64-key sub-steps, S[b] at b*64, O at 128).
+#include <limits.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "kocr_common.cuh"
@@ -112,6 +116,30 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   uint64_t r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
+}
+
+// Maximum of N values held in registers as a 3-ary tree of FMNMX3 (depth 4 for 80 values): every index is a compile-time constant
+template <int N, typename T>
+__device__ __forceinline__ float max_tree(const T* v) {
+  auto f = [](T x) -> float {
+    if constexpr (sizeof(T) == 4 && !std::is_same<T, float>::value) return __uint_as_float(x);
+    else return x;
+  };
+  if constexpr (N == 1) {
+    return f(v[0]);
+  } else if constexpr (N == 2) {
+    return fmaxf(f(v[0]), f(v[1]));
+  } else if constexpr (N == 3) {
+    return max3(f(v[0]), f(v[1]), f(v[2]));
+  } else {
+    constexpr int M = (N + 2) / 3;
+    float u[M];
+#pragma unroll
+    for (int g = 0; g < N / 3; ++g) u[g] = max3(f(v[3 * g]), f(v[3 * g + 1]), f(v[3 * g + 2]));
+    if constexpr (N % 3 == 1) u[M - 1] = f(v[N - 1]);
+    if constexpr (N % 3 == 2) u[M - 1] = fmaxf(f(v[N - 2]), f(v[N - 1]));
+    return max_tree<M, float>(u);
+  }
 }
 
 template <int N>
@@ -518,6 +546,338 @@ int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wor
   return KOCR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Experimental shape (KOCR_ATTN3=1, full attention only): THREE query tiles per CTA with single-buffered scores. TMEM: S_t (80
+// columns, P written over its first 40) and O_t (80) per tile = 480 columns. Three softmax warps per scheduler instead of two;
+// in exchange a tile's next scores can only be issued behind P_t.V of the current sub-step, so each tile's chain contains the
+// tensor pipe's latency and the other two tiles have to cover it. 512 threads: warp 0 TMA, warps 1-3 MMA (one per tile),
+// warps 4-15 softmax (tile = (warp - 4) / 4, lane quarter = warp % 4).
+struct Attn3 {
+#ifndef KOCR_A3_STAGES
+#define KOCR_A3_STAGES 4
+#endif
+  static constexpr int kSub = 80, kTiles = 3, kStages = KOCR_A3_STAGES;
+  static constexpr int kKvChunkBytes = kSub * 32, kKvTileBytes = kChunks * kKvChunkBytes;
+  static constexpr int kThreads = 128 + 128 * kTiles;
+  static constexpr int kSmem = kTiles * kTileBytes + 2 * kStages * kKvTileBytes + 512 + 1024;
+  __host__ __device__ static constexpr int s_col(int t) { return t * 160; }
+  __host__ __device__ static constexpr int o_col(int t) { return t * 160 + 80; }
+};
+
+__global__ void __launch_bounds__(Attn3::kThreads, 1)
+attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, __nv_bfloat16* __restrict__ out,
+                  const AttnWork* __restrict__ work, int num_heads) {
+  constexpr int kTiles = Attn3::kTiles, kKvStages = Attn3::kStages, kSub = Attn3::kSub;
+  constexpr int kKvChunkBytes = Attn3::kKvChunkBytes, kKvTileBytes = Attn3::kKvTileBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem_q + kTiles * kTileBytes;
+  uint8_t* smem_v = smem_k + kKvStages * kKvTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKvStages * kKvTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kKvStages;
+  uint64_t* v_full = k_empty + kKvStages;
+  uint64_t* v_empty = v_full + kKvStages;
+  uint64_t* s_full = v_empty + kKvStages;  // [tile]
+  uint64_t* p_full = s_full + kTiles;      // [tile]
+  uint64_t* o_last = p_full + kTiles;      // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_last + kTiles);
+
+  const int warp = (int)uniform_u32(threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const AttnWork w = work[blockIdx.x];
+  const int head = blockIdx.y;
+  const int n_sub = (w.kv_len + kSub - 1) / kSub;
+  const int col_q = head * 3 * kHd, col_k = col_q + kHd, col_v = col_q + 2 * kHd;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], kTiles);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], kTiles);
+    }
+    for (int t = 0; t < kTiles; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&o_last[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<64>();
+    if (warp == 0) {
+      const int kv_begin = (int)uniform_u32(w.kv_begin), q_begin = (int)uniform_u32(w.q_begin);
+      const int n_sub_u = (int)uniform_u32(n_sub);
+      if (elect_one()) {
+        mbar_expect_tx(q_full, kTiles * kTileBytes);
+        for (int t = 0; t < kTiles; ++t)
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_q, q_full, col_q + c * 16, q_begin + t * kTileRows);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_sub_u; ++j) {
+        const int s = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        const int row = kv_begin + j * kSub;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[s], kKvTileBytes);
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_k + s * kKvTileBytes + c * kKvChunkBytes, &tm_kv, &k_full[s], col_k + c * 16, row);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[s], kKvTileBytes);
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_2d(smem_v + s * kKvTileBytes + c * kKvChunkBytes, &tm_kv, &v_full[s], col_v + c * 16, row);
+        }
+        __syncwarp();
+      }
+    } else {
+      // MMA issuer of query tile t = warp - 1: S_t(0); then per sub-step P_t(i).V followed at once by S_t(i+1) - the tensor pipe
+      // runs them in order, so the scores may overwrite P the moment P.V has read it
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd, 0, 1);
+      constexpr uint32_t hi32 = smem_desc_hi(256, 6);
+      const int t = warp - 1;
+      const uint32_t tmem_u = uniform_u32(tmem_base);
+      const int n_sub_u = (int)uniform_u32(n_sub);
+      const uint32_t q_lo = smem_desc_lo(smem_u32(smem_q), 16) + t * (kTileBytes >> 4);
+      const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
+      const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kKvChunkBytes);
+      const uint32_t d_s = tmem_u + Attn3::s_col(t), d_o = tmem_u + Attn3::o_col(t);
+      auto issue_s = [&](int i) {
+        const int s = i % kKvStages;
+        mbar_wait(&k_full[s], (i / kKvStages) & 1);
+        tc_fence_after();
+        const uint32_t ka = k_lo + s * (kKvTileBytes >> 4);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+          umma_ss_lo(d_s, q_lo + c * (kChunkBytes >> 4), ka + c * (kKvChunkBytes >> 4), hi32, idesc_s, c != 0);
+        tc_commit_elect(&s_full[t]);
+        tc_commit_elect(&k_empty[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int i = 0; i < n_sub_u; ++i) {
+        const int s = i % kKvStages;
+        mbar_wait(&v_full[s], (i / kKvStages) & 1);
+        if (i + 1 < n_sub_u) mbar_wait(&k_full[(i + 1) % kKvStages], ((i + 1) / kKvStages) & 1);  // off the critical path: before P arrives
+        mbar_wait(&p_full[t], i & 1);
+        tc_fence_after();
+        const uint32_t va = v_lo + s * (kKvTileBytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < kSub / 16; ++ks)
+          umma_ts_lo(d_o, d_s + ks * 8, va + ks * (512 >> 4), hi32, idesc_o, (i > 0 || ks != 0));
+        tc_commit_elect(&v_empty[s]);
+        if (i + 1 < n_sub_u) issue_s(i + 1);
+        else tc_commit_elect(&o_last[t]);
+      }
+    }
+  } else {
+    setmaxnreg_inc<144>();
+    const int t = (warp - 4) >> 2;
+    const int qtr = warp & 3;
+    const int r = qtr * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+    const uint32_t t_s = tmem_base + Attn3::s_col(t) + lane_off;
+    const uint32_t t_o = tmem_base + Attn3::o_col(t) + lane_off;
+    float m_ref = -INFINITY, l = 0.f;
+#ifndef KOCR_PP3
+#define KOCR_PP3 0
+#endif
+    // exponent-phase token around the three tiles' warps of one lane quarter (same scheduler, same MUFU unit): 0 -> 1 -> 2 -> 0
+    constexpr bool kPP3 = KOCR_PP3;
+#ifndef KOCR_A3_POLY
+#define KOCR_A3_POLY 4
+#endif
+    constexpr int kPoly3 = KOCR_A3_POLY;
+    const int pp_mine = 1 + t * 4 + qtr, pp_next = 1 + ((t + 1) % kTiles) * 4 + qtr;
+    if (kPP3 && t == kTiles - 1) named_bar_arrive(pp_next, 64);  // tile 0 goes first
+    for (int i = 0; i < n_sub; ++i) {
+      mbar_wait(&s_full[t], i & 1);  // S_t(i) complete; it was issued behind P_t(i-1).V, which is therefore complete as well
+      tc_fence_after();
+      uint32_t sr[kSub];
+      tmem_ld_x32(t_s, sr);
+      tmem_ld_x32(t_s + 32, sr + 32);
+      tmem_ld_x16(t_s + 64, sr + 64);
+      tc_wait_ld();
+      const int valid = w.kv_len - i * kSub;
+      if (valid < kSub) {
+#pragma unroll
+        for (int c = 0; c < kSub; ++c)
+          if (c >= valid) sr[c] = 0xff800000u;
+      }
+#ifndef KOCR_A3_TREE
+#define KOCR_A3_TREE 0
+#endif
+      float mx;
+      if constexpr (KOCR_A3_TREE) {
+        mx = max_tree<kSub, uint32_t>(sr);
+      } else {
+        float mxa[kSub / 16];
+#pragma unroll
+        for (int g = 0; g < kSub / 16; ++g) {
+          mxa[g] = max3(__uint_as_float(sr[16 * g]), __uint_as_float(sr[16 * g + 1]), __uint_as_float(sr[16 * g + 2]));
+#pragma unroll
+          for (int c = 3; c < 15; c += 2) mxa[g] = max3(mxa[g], __uint_as_float(sr[16 * g + c]), __uint_as_float(sr[16 * g + c + 1]));
+          mxa[g] = fmaxf(mxa[g], __uint_as_float(sr[16 * g + 15]));
+        }
+        mx = mxa[0];
+#pragma unroll
+        for (int g = 1; g < kSub / 16; ++g) mx = fmaxf(mx, mxa[g]);
+      }
+      float alpha = 1.0f;
+      const bool grow = mx > m_ref + kRescaleThreshold;
+      if (grow) {
+        alpha = ex2(m_ref - mx);
+        m_ref = mx;
+      }
+      float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      if (kPP3) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");
+      const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
+      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pk[kSub / 2];
+#pragma unroll
+      for (int c = 0; c < kSub / 2; ++c) {
+        const uint64_t x2 = add_f32x2(pack_u32x2(sr[2 * c], sr[2 * c + 1]), neg_m2);
+        uint64_t p2;
+        if (kPoly3 > 0 && (c % kPoly3) == kPoly3 - 1) {
+          p2 = ex2_poly_f32x2(x2);
+        } else {
+          float x0, x1;
+          unpack_f32x2(x2, x0, x1);
+          p2 = pack_f32x2(ex2(x0), ex2(x1));
+        }
+        acc2[c & 3] = add_f32x2(acc2[c & 3], p2);
+        float p0, p1;
+        unpack_f32x2(p2, p0, p1);
+        pk[c] = pack_bf16(p0, p1);
+        if (kPP3 && c == kPpAt && (t != kTiles - 1 || i + 1 < n_sub)) named_bar_arrive(pp_next + (int)(pk[c] >> 31), 64);
+#ifndef KOCR_A3_EARLYST
+#define KOCR_A3_EARLYST 0
+#endif
+        if (KOCR_A3_EARLYST && c == 15) tmem_st_x16(t_s, pk);       // P leaves in pieces: the stores' latency overlaps the remaining exponents
+        if (KOCR_A3_EARLYST && c == 31) tmem_st_x16(t_s + 16, pk + 16);
+      }
+      float sum;
+      {
+        float a0, a1, b0, b1;
+        unpack_f32x2(add_f32x2(acc2[0], acc2[1]), a0, a1);
+        unpack_f32x2(add_f32x2(acc2[2], acc2[3]), b0, b1);
+        sum = (a0 + a1) + (b0 + b1);
+      }
+      l = l * alpha + sum;
+      if (!KOCR_A3_EARLYST) {
+        tmem_st_x16(t_s, pk);
+        tmem_st_x16(t_s + 16, pk + 16);
+      }
+      tmem_st_x8(t_s + 32, pk + 32);
+      if (i > 0 && __any_sync(0xffffffffu, grow)) {  // P_t(i-1).V is complete (see the wait above): O_t may be rescaled right away
+        uint32_t o[kHd];
+        tmem_ld_cols<kHd>(t_o, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < kHd; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+        tmem_st_cols<kHd>(t_o, o);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    mbar_wait(&o_last[t], 0);
+    tc_fence_after();
+    uint32_t o[kHd];
+    tmem_ld_cols<kHd>(t_o, o);
+    tc_wait_ld();
+    const float inv = 1.0f / l;
+    const int qrow = t * kTileRows + r;
+    if (qrow < w.q_rows) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(w.q_begin + qrow) * (num_heads * kHd) + head * kHd);
+#pragma unroll
+      for (int c = 0; c < kHd / 8; ++c) {
+        const uint32_t* x = o + c * 8;
+        dst[c] = make_uint4(pack_bf16(__uint_as_float(x[0]) * inv, __uint_as_float(x[1]) * inv),
+                            pack_bf16(__uint_as_float(x[2]) * inv, __uint_as_float(x[3]) * inv),
+                            pack_bf16(__uint_as_float(x[4]) * inv, __uint_as_float(x[5]) * inv),
+                            pack_bf16(__uint_as_float(x[6]) * inv, __uint_as_float(x[7]) * inv));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int launch_attention3(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_work, int n_work, int num_heads, int64_t total_rows,
+                             cudaStream_t stream) {
+  CUtensorMap tm_q, tm_kv;
+  uint64_t dims[2] = {(uint64_t)num_heads * 3 * kHd, (uint64_t)total_rows};
+  uint64_t str[1] = {(uint64_t)num_heads * 3 * kHd * 2};
+  uint32_t box_q[2] = {16, kTileRows}, box_kv[2] = {16, (uint32_t)Attn3::kSub};
+  int rc = make_tensor_map(&tm_q, qkv, 2, dims, str, box_q, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (rc) return rc;
+  rc = make_tensor_map(&tm_kv, qkv, 2, dims, str, box_kv, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (rc) return rc;
+  if ((rc = ctx->opt_in_smem(reinterpret_cast<const void*>(&attention3_kernel), Attn3::kSmem))) return rc;
+  dim3 grid((unsigned)n_work, (unsigned)num_heads);
+  attention3_kernel<<<grid, Attn3::kThreads, Attn3::kSmem, stream>>>(tm_q, tm_kv, static_cast<__nv_bfloat16*>(out), d_work, num_heads);
+  KOCR_LAUNCH_CHECK("attention3_kernel");
+  return KOCR_OK;
+}
+
+// Host: split every sequence into 384-row blocks for the three-tile kernel and at most two 256-row blocks for the two-tile one,
+// whichever combination pads the least (a 6624-row letter page = 16 x 384 + 2 x 240: 0.5 % padding instead of 4.2 % for 18 x 384)
+int build_attn_work_mixed(const int32_t* cu, int n_seqs, std::vector<AttnWork>* w3, std::vector<AttnWork>* w2) {
+  w3->clear();
+  w2->clear();
+  constexpr int kB3 = 3 * kTileRows, kB2 = 2 * kTileRows;
+  for (int i = 0; i < n_seqs; ++i) {
+    const int b = cu[i], len = cu[i + 1] - cu[i];
+    if (len <= 0) return fail(KOCR_ERR_INVALID, "attention: empty or negative sequence");
+    int na = 0, nb = 0, best_pad = INT32_MAX;
+    for (int tb = 0; tb <= 2; ++tb) {
+      const int rest = len - tb * kB2;
+      const int ta = rest > 0 ? (rest + kB3 - 1) / kB3 : 0;
+      const int pad = ta * kB3 + tb * kB2 - len;
+      if (pad >= 0 && pad < best_pad) { best_pad = pad; na = ta; nb = tb; }
+    }
+    int q = 0;
+    for (int k = 0; k < na; ++k) {  // full blocks when two-tile blocks follow (they take the remainder), else the last one is short
+      const int rows = std::min(kB3, len - q);
+      w3->push_back(AttnWork{b + q, rows, b, len});
+      q += rows;
+    }
+    for (int k = 0; k < nb; ++k) {  // the remainder, spread evenly
+      const int rows = (len - q + (nb - k) - 1) / (nb - k);
+      w2->push_back(AttnWork{b + q, rows, b, len});
+      q += rows;
+    }
+    if (q != len) return fail(KOCR_ERR_INVALID, "attention: work split does not cover the sequence");
+  }
+  // longest sequences first: their blocks are the longest-running CTAs, the short ones fill the tail of the launch
+  auto by_len = [](const AttnWork& x, const AttnWork& y) { return x.kv_len > y.kv_len; };
+  std::stable_sort(w3->begin(), w3->end(), by_len);
+  std::stable_sort(w2->begin(), w2->end(), by_len);
+  return KOCR_OK;
+}
+
 // Host: split sequences into 256-row query blocks (one CTA each per head)
 int build_attn_work(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out) {
   out->clear();
@@ -565,16 +925,21 @@ extern "C" int kocr_op_attention(KocrCtx* ctx_, const void* qkv, void* out, cons
   if (!ctx || !qkv || !out || !cu_seqlens_host || n_seqs <= 0) return fail(KOCR_ERR_INVALID, "kocr_op_attention: bad argument");
   if (head_dim != kHd) return fail(KOCR_ERR_UNSUPPORTED, "kocr_op_attention: kernels are built for head_dim 80");
   reset_launch_count();
-  std::vector<AttnWork> work;
-  int rc = build_attn_work(cu_seqlens_host, n_seqs, &work);
+  std::vector<AttnWork> work, work3;
+  static const bool two_tile_only = getenv("KOCR_ATTN2") != nullptr;  // A/B switch: the two-tile kernel alone
+  int rc = two_tile_only ? build_attn_work(cu_seqlens_host, n_seqs, &work) : build_attn_work_mixed(cu_seqlens_host, n_seqs, &work3, &work);
   if (rc) return rc;
+  std::vector<AttnWork> all(work3);
+  all.insert(all.end(), work.begin(), work.end());
   void* d_work;
   int slot = -1;
-  rc = ctx->stage(work.data(), work.size() * sizeof(AttnWork), stream, &d_work, &slot);
+  rc = ctx->stage(all.data(), all.size() * sizeof(AttnWork), stream, &d_work, &slot);
   if (rc) return rc;
-  StageGuard guard(ctx, slot, stream);  // released after the kernel that reads the work list is enqueued
-  return launch_attention(ctx, qkv, out, static_cast<const AttnWork*>(d_work), (int)work.size(), num_heads,
-                          cu_seqlens_host[n_seqs], stream, nullptr);
+  StageGuard guard(ctx, slot, stream);  // released after the kernels that read the work list are enqueued
+  const AttnWork* dw = static_cast<const AttnWork*>(d_work);
+  if (!work3.empty() && (rc = launch_attention3(ctx, qkv, out, dw, (int)work3.size(), num_heads, cu_seqlens_host[n_seqs], stream))) return rc;
+  if (work.empty()) return KOCR_OK;
+  return launch_attention(ctx, qkv, out, dw + work3.size(), (int)work.size(), num_heads, cu_seqlens_host[n_seqs], stream, nullptr);
 }
 
 #ifdef KOCR_TRACE

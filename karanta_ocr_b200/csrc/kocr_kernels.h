@@ -59,4 +59,8 @@ struct AttnWork { int q_begin; int q_rows; int kv_begin; int kv_len; };  // one 
 int launch_attention(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_work, int n_work, int num_heads,
                      int64_t total_rows, cudaStream_t stream, const int2* d_win = nullptr);
 
+// full attention, three query tiles per CTA (384-row blocks); launch_attention (two tiles) takes what build_attn_work_mixed leaves it
+int launch_attention3(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_work, int n_work, int num_heads, int64_t total_rows,
+                      cudaStream_t stream);
+
 }  // namespace kocr

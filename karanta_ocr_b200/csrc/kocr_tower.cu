@@ -17,6 +17,7 @@
 namespace kocr {
 
 int build_attn_work(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out);
+int build_attn_work_mixed(const int32_t* cu, int n_seqs, std::vector<AttnWork>* w3, std::vector<AttnWork>* w2);
 int build_attn_work_windowed(const int32_t* cu, int n_seqs, const int32_t* cu_win, int n_win, std::vector<AttnWork>* out,
                              std::vector<int32_t>* row_win);
 
@@ -34,8 +35,8 @@ struct Plan {
   std::vector<int64_t> key;  // grid_thw, flattened
   uint8_t* d = nullptr;      // device tables
   size_t cap = 0;            // bytes allocated at d
-  size_t off_pos = 0, off_wf = 0, off_ww = 0, off_wi = 0, off_rw = 0;
-  int S = 0, max_pos = 0, n_work_full = 0, n_work_win = 0;
+  size_t off_pos = 0, off_wf = 0, off_w3 = 0, off_ww = 0, off_wi = 0, off_rw = 0;
+  int S = 0, max_pos = 0, n_work_full = 0, n_work3 = 0, n_work_win = 0;  // full attention: n_work3 three-tile blocks + n_work_full two-tile blocks
   cudaEvent_t used = nullptr;       // recorded after the last forward that reads the tables was enqueued
   cudaStream_t last_stream = nullptr;
   bool multi_stream = false;
@@ -176,14 +177,15 @@ static int get_plan(Tower* t, const int64_t* grid_thw, int n_images, cudaStream_
     for (int g = 0; g < S / 4; ++g) memcpy(&p2[(size_t)g * 8], &pos[(size_t)widx[g] * 8], 8 * sizeof(int32_t));
     pos.swap(p2);
   }
-  std::vector<AttnWork> work_full, work_win;
-  if ((rc = build_attn_work(cu.data(), n_cu - 1, &work_full))) return rc;
+  std::vector<AttnWork> work_full, work3, work_win;
+  if ((rc = build_attn_work_mixed(cu.data(), n_cu - 1, &work3, &work_full))) return rc;
   std::vector<int32_t> row_win;
   if (t->q25 && (rc = build_attn_work_windowed(cu.data(), n_cu - 1, cuw.data(), n_cuw - 1, &work_win, &row_win))) return rc;
 
   const size_t off_pos = 0;
   const size_t off_wf = align256(pos.size() * 4);
-  const size_t off_ww = off_wf + align256(work_full.size() * sizeof(AttnWork));
+  const size_t off_w3 = off_wf + align256(work_full.size() * sizeof(AttnWork));
+  const size_t off_ww = off_w3 + align256(work3.size() * sizeof(AttnWork));
   const size_t off_wi = off_ww + align256(work_win.size() * sizeof(AttnWork));
   const size_t off_rw = off_wi + align256(widx.size() * 4);
   const size_t total = off_rw + align256(row_win.size() * 4);
@@ -217,15 +219,16 @@ static int get_plan(Tower* t, const int64_t* grid_thw, int n_images, cudaStream_
   if ((rc = ctx->stage_begin(total, &hs, &slot))) return rc;
   uint8_t* hb = static_cast<uint8_t*>(hs);
   memcpy(hb + off_pos, pos.data(), pos.size() * 4);
-  memcpy(hb + off_wf, work_full.data(), work_full.size() * sizeof(AttnWork));
+  if (!work_full.empty()) memcpy(hb + off_wf, work_full.data(), work_full.size() * sizeof(AttnWork));
+  if (!work3.empty()) memcpy(hb + off_w3, work3.data(), work3.size() * sizeof(AttnWork));
   if (!work_win.empty()) memcpy(hb + off_ww, work_win.data(), work_win.size() * sizeof(AttnWork));
   if (!widx.empty()) memcpy(hb + off_wi, widx.data(), widx.size() * 4);
   if (!row_win.empty()) memcpy(hb + off_rw, row_win.data(), row_win.size() * 4);
   cudaError_t e = cudaMemcpyAsync(p->d, hs, total, cudaMemcpyHostToDevice, st);
   ctx->stage_release(slot, st);  // the pinned slot's only reader is this copy
   if (e != cudaSuccess) return fail(KOCR_ERR_CUDA, cudaGetErrorString(e));
-  p->off_pos = off_pos; p->off_wf = off_wf; p->off_ww = off_ww; p->off_wi = off_wi; p->off_rw = off_rw;
-  p->S = S; p->max_pos = max_pos; p->n_work_full = (int)work_full.size(); p->n_work_win = (int)work_win.size();
+  p->off_pos = off_pos; p->off_wf = off_wf; p->off_w3 = off_w3; p->off_ww = off_ww; p->off_wi = off_wi; p->off_rw = off_rw;
+  p->S = S; p->max_pos = max_pos; p->n_work_full = (int)work_full.size(); p->n_work3 = (int)work3.size(); p->n_work_win = (int)work_win.size();
   p->last_stream = st;
   p->multi_stream = false;
   p->tick = ++t->plan_tick;
@@ -536,10 +539,11 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
   const uint8_t* db = plan->d;
   const int2* d_pos = reinterpret_cast<const int2*>(db + plan->off_pos);
   const AttnWork* d_wf = reinterpret_cast<const AttnWork*>(db + plan->off_wf);
+  const AttnWork* d_w3 = reinterpret_cast<const AttnWork*>(db + plan->off_w3);
   const AttnWork* d_ww = reinterpret_cast<const AttnWork*>(db + plan->off_ww);
   const int32_t* d_wi = reinterpret_cast<const int32_t*>(db + plan->off_wi);
   const int2* d_rw = reinterpret_cast<const int2*>(db + plan->off_rw);
-  const int n_work_full = plan->n_work_full, n_work_win = plan->n_work_win;
+  const int n_work_full = plan->n_work_full, n_work3 = plan->n_work3, n_work_win = plan->n_work_win;
 
   // ---- patch embed (HF :304-310; Conv3d with kernel == stride is a GEMM over the flattened patch)
   const void* pv = pixel_values;
@@ -582,8 +586,12 @@ int kocr_tower_forward(KocrTower* tower, const void* pixel_values, int pv_dtype,
     }
     {
       ProfScope ps(ctx, full ? kProfAttention : kProfAttentionWin, st);
-      if (full) rc = launch_attention(ctx, qkv, attn, d_wf, n_work_full, H, S, st);
-      else rc = launch_attention(ctx, qkv, attn, d_ww, n_work_win, H, S, st, d_rw);
+      if (full) {  // 384-row blocks on the three-tile kernel, what they leave (at most two blocks per sequence) on the two-tile one
+        if (n_work3) rc = launch_attention3(ctx, qkv, attn, d_w3, n_work3, H, S, st);
+        if (!rc && n_work_full) rc = launch_attention(ctx, qkv, attn, d_wf, n_work_full, H, S, st);
+      } else {
+        rc = launch_attention(ctx, qkv, attn, d_ww, n_work_win, H, S, st, d_rw);
+      }
       if (rc) return rc;
     }
     GemmEpilogue e2{};

@@ -132,3 +132,32 @@ def test_largest_page_vs_oracle(backend, shape):
     g = out["image_grid_thw"].numpy()
     assert np.array_equal(g, ref_grid) and 60000 < int(g[0, 1] * g[0, 2]) <= 65536
     assert np.array_equal(out["pixel_values"].numpy(), ref_pv)
+
+
+@pytest.mark.parametrize("backend", ["torchvision", "pil"])
+@pytest.mark.parametrize("layout", ["chw", "hwc", "gray"])
+@pytest.mark.parametrize("h,w,maxp,what", [
+    (308, 560, CKPT_MAX, "no resize at all: copy path, no vertical pass"),
+    (300, 560, CKPT_MAX, "vertical taps only (copy path + pass 2)"),
+    (308, 555, CKPT_MAX, "horizontal up by 1 %: four columns per thread"),
+    (308, 570, CKPT_MAX, "horizontal down by 2 %: four columns per thread, window starts up to 4 apart"),
+    (600, 800, 213000, "both axes down by ~1.5: two columns per thread"),
+    (600, 800, 100000, "both axes down by ~2.2: generic tap loops"),
+    (90, 3000, CKPT_MAX, "wide strip: many column tiles, last tile narrower"),
+])
+def test_every_horizontal_pass_variant_vs_oracle(backend, layout, h, w, maxp, what):
+    """The horizontal pass has four shapes (copy, 4 / 2 adjacent columns per thread, generic loops) chosen per page from its
+    tap table; each is held bit-exact to the oracle for both resize arithmetics and the three input layouts."""
+    rng = np.random.default_rng(h * 7919 + w)
+    chw = rng.integers(0, 256, (3, h, w), dtype=np.uint8)
+    if layout == "gray":
+        chw = np.repeat(chw[:1], 3, axis=0)
+        img = chw[0]
+    elif layout == "hwc":
+        img = np.ascontiguousarray(chw.transpose(1, 2, 0))
+    else:
+        img = chw
+    out = _proc(backend, maxp)(images=[img])
+    ref_pv, ref_grid = po.preprocess([chw], 3136, maxp, MODES[backend])
+    assert np.array_equal(out["image_grid_thw"].numpy(), ref_grid), what
+    assert np.array_equal(out["pixel_values"].numpy(), ref_pv), what

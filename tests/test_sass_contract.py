@@ -43,7 +43,7 @@ def test_only_sm100a_code_is_embedded():
 
 
 def test_gemm_and_attention_use_tcgen05_tmem_tma(sass):
-    for frag in ("gemm_kernel", "attention_kernel"):
+    for frag in ("gemm_kernel", "attention_kernel", "attention3_kernel"):
         for body in _of(sass, frag):
             text = "\n".join(body)
             assert "UTCHMMA" in text, f"{frag}: no tcgen05.mma"

@@ -15,12 +15,12 @@ print(d['roofline']); print(d['preprocess_hbm'])
 PY
 [ "$2" == "--no-reference" ] || python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference exit $?"; cut -c1-400 gpurun_out/bench_reference.json
 # launch list of the bench command itself (hot-path kernels only; weight prepack launches filtered out)
-python bench.py --steps 1 --warmup 1 --pages 8 --no-cpu-baseline --no-library-baselines > gpurun_out/plain_p8.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_kernel|attention_kernel|norm_kernel|preprocess_kernel|cast_f32|gather_groups" -c 1200 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 1 --pages 8 --no-cpu-baseline --no-library-baselines > gpurun_out/ncu_launches.log 2>&1
+python bench.py --steps 1 --warmup 1 --pages 8 --no-cpu-baseline --no-library-baselines --no-c5 > gpurun_out/plain_p8.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_kernel|attention|norm_kernel|preprocess_kernel|cast_f32|gather_groups" -c 1200 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 1 --pages 8 --no-cpu-baseline --no-library-baselines --no-c5 > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 # full counters, one launch of each hot kernel at the C2 batch size (64 pages, depth 1)
 python tools/prof_target.py 64 > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none -k regex:"attention_kernel|preprocess_kernel|gemm_kernel|^norm_kernel|kocr::norm_kernel" -s 10 -c 10 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
+ncu --set full --clock-control none -k regex:"attention|preprocess_kernel|gemm_kernel|^norm_kernel|kocr::norm_kernel" -s 11 -c 11 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
 echo "ncu full exit $?"
 # the raw page travels back as csv; the report itself only if it is small enough for the 64 MiB return limit
 ncu -i gpurun_out/prof_final.ncu-rep --page raw --csv > gpurun_out/prof_final_raw.csv 2>/dev/null

@@ -17,8 +17,10 @@ NCU = "/usr/local/cuda/bin/ncu"
 
 # kernel (template arguments included) -> bench.py profile class, for the depth-1 Qwen2-VL target
 def classify(name, seen):
+    if "attention3_kernel" in name:
+        return "attention3"      # full attention, three query tiles per CTA (384-row blocks)
     if "attention_kernel" in name:
-        return "attention"
+        return "attention2"      # two-tile kernel: the remainder blocks of every sequence
     if "preprocess_kernel" in name:
         return "preprocess"
     if "norm_kernel" in name and "fold" not in name:
@@ -103,10 +105,16 @@ def full_summary(rep):
     def to_ms(r):
         v, u = float(r[ci["gpu__time_duration.sum"]].replace(",", "")), units[ci["gpu__time_duration.sum"]].lower()
         return v * {"ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}[u]
+    # bench.py's class "attention" = both kernels of a full-attention layer
+    def both(fn):
+        return sum(fn(last[k]) for k in ("attention3", "attention2") if k in last)
     tj = {"source": "ncu --set full --clock-control none, tools/prof_target.py 64 (C2 batch: 64 letter pages, Qwen2-VL-7B widths, depth 1), "
                     "warm launch of each kernel; profiles/r2_ncu_full_kernels_pages64.csv",
           "dram_bytes_per_launch": {k: int(to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) for k, r in last.items()},
           "ncu_ms_per_launch": {k: to_ms(r) for k, r in last.items()}}
+    if "attention3" in last or "attention2" in last:
+        tj["dram_bytes_per_launch"]["attention"] = int(both(lambda r: to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")))
+        tj["ncu_ms_per_launch"]["attention"] = both(to_ms)
     out = os.path.join(PROF, "r2_traffic.json")
     json.dump(tj, open(out, "w"), indent=1)
     print("wrote", out)
