@@ -591,6 +591,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   const int head = blockIdx.y;
   const int n_sub = (w.kv_len + kSub - 1) / kSub;
   const int col_q = head * 3 * kHd, col_k = col_q + kHd, col_v = col_q + 2 * kHd;
+  // a sequence's last block may hold fewer than 384 rows: tiles without a valid row do nothing at all (their MMA and softmax
+  // warps go straight to the final barrier), so the block costs what its active tiles cost and stays next to its sequence's
+  // other blocks in time - they share K/V through L2
+  const int n_act = (w.q_rows + kTileRows - 1) / kTileRows;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -598,9 +602,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], kTiles);
+      mbar_init(&k_empty[s], n_act);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], kTiles);
+      mbar_init(&v_empty[s], n_act);
     }
     for (int t = 0; t < kTiles; ++t) {
       mbar_init(&s_full[t], 1);
@@ -620,9 +624,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     if (warp == 0) {
       const int kv_begin = (int)uniform_u32(w.kv_begin), q_begin = (int)uniform_u32(w.q_begin);
       const int n_sub_u = (int)uniform_u32(n_sub);
+      const int n_act_u = (int)uniform_u32(n_act);
       if (elect_one()) {
-        mbar_expect_tx(q_full, kTiles * kTileBytes);
-        for (int t = 0; t < kTiles; ++t)
+        mbar_expect_tx(q_full, n_act_u * kTileBytes);
+        for (int t = 0; t < n_act_u; ++t)
           for (int c = 0; c < kChunks; ++c)
             tma_load_2d(smem_q + t * kTileBytes + c * kChunkBytes, &tm_q, q_full, col_q + c * 16, q_begin + t * kTileRows);
       }
@@ -646,7 +651,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
         __syncwarp();
       }
-    } else {
+    } else if (warp - 1 < (int)uniform_u32(n_act)) {
       // MMA issuer of query tile t = warp - 1: S_t(0); then per sub-step P_t(i).V followed at once by S_t(i+1) - the tensor pipe
       // runs them in order, so the scores may overwrite P the moment P.V has read it
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);
@@ -690,6 +695,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   } else {
     setmaxnreg_inc<144>();
     const int t = (warp - 4) >> 2;
+    if (t < n_act) {
     const int qtr = warp & 3;
     const int r = qtr * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
@@ -816,6 +822,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                             pack_bf16(__uint_as_float(x[6]) * inv, __uint_as_float(x[7]) * inv));
       }
     }
+    }  // active tile
   }
   tc_fence_before();
   __syncthreads();
@@ -842,8 +849,20 @@ int launch_attention3(Ctx* ctx, const void* qkv, void* out, const AttnWork* d_wo
   return KOCR_OK;
 }
 
-// Host: split every sequence into 384-row blocks for the three-tile kernel and at most two 256-row blocks for the two-tile one,
-// whichever combination pads the least (a 6624-row letter page = 16 x 384 + 2 x 240: 0.5 % padding instead of 4.2 % for 18 x 384)
+// Host: full attention = 384-row blocks on the three-tile kernel; a sequence's last block holds what is left (tiles without rows
+// are skipped by the kernel). build_attn_work_mixed (three-tile blocks plus up to two 256-row blocks for the two-tile kernel) pads
+// less but makes a second launch that re-reads every sequence's K/V from HBM (ncu: +2.9 GB per layer): kept for A/B runs only.
+int build_attn_work3(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out) {
+  out->clear();
+  for (int i = 0; i < n_seqs; ++i) {
+    const int b = cu[i], len = cu[i + 1] - cu[i];
+    if (len <= 0) return fail(KOCR_ERR_INVALID, "attention: empty or negative sequence");
+    for (int q = 0; q < len; q += 3 * kTileRows) out->push_back(AttnWork{b + q, std::min(3 * kTileRows, len - q), b, len});
+  }
+  std::stable_sort(out->begin(), out->end(), [](const AttnWork& x, const AttnWork& y) { return x.kv_len > y.kv_len; });
+  return KOCR_OK;
+}
+
 int build_attn_work_mixed(const int32_t* cu, int n_seqs, std::vector<AttnWork>* w3, std::vector<AttnWork>* w2) {
   w3->clear();
   w2->clear();
@@ -926,8 +945,11 @@ extern "C" int kocr_op_attention(KocrCtx* ctx_, const void* qkv, void* out, cons
   if (head_dim != kHd) return fail(KOCR_ERR_UNSUPPORTED, "kocr_op_attention: kernels are built for head_dim 80");
   reset_launch_count();
   std::vector<AttnWork> work, work3;
-  static const bool two_tile_only = getenv("KOCR_ATTN2") != nullptr;  // A/B switch: the two-tile kernel alone
-  int rc = two_tile_only ? build_attn_work(cu_seqlens_host, n_seqs, &work) : build_attn_work_mixed(cu_seqlens_host, n_seqs, &work3, &work);
+  static const bool two_tile_only = getenv("KOCR_ATTN2") != nullptr;   // A/B switches: the two-tile kernel alone,
+  static const bool mixed = getenv("KOCR_ATTN_MIXED") != nullptr;       // three-tile blocks + two-tile remainder blocks
+  int rc = two_tile_only ? build_attn_work(cu_seqlens_host, n_seqs, &work)
+           : mixed       ? build_attn_work_mixed(cu_seqlens_host, n_seqs, &work3, &work)
+                         : build_attn_work3(cu_seqlens_host, n_seqs, &work3);
   if (rc) return rc;
   std::vector<AttnWork> all(work3);
   all.insert(all.end(), work.begin(), work.end());

@@ -17,7 +17,7 @@
 namespace kocr {
 
 int build_attn_work(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out);
-int build_attn_work_mixed(const int32_t* cu, int n_seqs, std::vector<AttnWork>* w3, std::vector<AttnWork>* w2);
+int build_attn_work3(const int32_t* cu, int n_seqs, std::vector<AttnWork>* out);
 int build_attn_work_windowed(const int32_t* cu, int n_seqs, const int32_t* cu_win, int n_win, std::vector<AttnWork>* out,
                              std::vector<int32_t>* row_win);
 
@@ -178,7 +178,7 @@ static int get_plan(Tower* t, const int64_t* grid_thw, int n_images, cudaStream_
     pos.swap(p2);
   }
   std::vector<AttnWork> work_full, work3, work_win;
-  if ((rc = build_attn_work_mixed(cu.data(), n_cu - 1, &work3, &work_full))) return rc;
+  if ((rc = build_attn_work3(cu.data(), n_cu - 1, &work3))) return rc;  // work_full (two-tile blocks) stays empty: see build_attn_work3
   std::vector<int32_t> row_win;
   if (t->q25 && (rc = build_attn_work_windowed(cu.data(), n_cu - 1, cuw.data(), n_cuw - 1, &work_win, &row_win))) return rc;
 

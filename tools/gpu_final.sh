@@ -20,7 +20,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_kernel|
 echo "ncu launches exit $?"
 # full counters, one launch of each hot kernel at the C2 batch size (64 pages, depth 1)
 python tools/prof_target.py 64 > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --clock-control none -k regex:"attention|preprocess_kernel|gemm_kernel|^norm_kernel|kocr::norm_kernel" -s 11 -c 11 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
+ncu --set full --clock-control none -k regex:"attention|preprocess_kernel|gemm_kernel|^norm_kernel|kocr::norm_kernel" -s 10 -c 10 -f -o gpurun_out/prof_final python tools/prof_target.py 64 > gpurun_out/prof_ncu.log 2>&1
 echo "ncu full exit $?"
 # the raw page travels back as csv; the report itself only if it is small enough for the 64 MiB return limit
 ncu -i gpurun_out/prof_final.ncu-rep --page raw --csv > gpurun_out/prof_final_raw.csv 2>/dev/null
