@@ -78,7 +78,7 @@ static constexpr float kRescaleThreshold = 8.0f;
 // Timeline trace of one CTA (variant builds with -DKOCR_TRACE only): lane 0 of every warp stamps clock64 at fixed points of each
 // sub-step; tools/attn_trace.py reads the stamps back and prints where each warp's time goes.
 #ifdef KOCR_TRACE
-static constexpr int kTraceSubs = 96, kTracePts = 12, kTraceWarps = 12;
+static constexpr int kTraceSubs = 96, kTracePts = 12, kTraceWarps = 16;
 __device__ long long g_attn_trace[kTraceWarps][kTraceSubs][kTracePts];
 #define KOCR_STAMP(i, pt)                                                                                     \
   do {                                                                                                        \
@@ -595,6 +595,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   // warps go straight to the final barrier), so the block costs what its active tiles cost and stays next to its sequence's
   // other blocks in time - they share K/V through L2
   const int n_act = (w.q_rows + kTileRows - 1) / kTileRows;
+#ifdef KOCR_TRACE
+  const bool trace_on = blockIdx.x == 13 && blockIdx.y == 5;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -664,10 +667,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16);
       const uint32_t v_lo = smem_desc_lo(smem_u32(smem_v), kKvChunkBytes);
       const uint32_t d_s = tmem_u + Attn3::s_col(t), d_o = tmem_u + Attn3::o_col(t);
-      auto issue_s = [&](int i) {
+      auto issue_s = [&](int i) {  // the caller has seen k_full of this tile
         const int s = i % kKvStages;
-        mbar_wait(&k_full[s], (i / kKvStages) & 1);
-        tc_fence_after();
         const uint32_t ka = k_lo + s * (kKvTileBytes >> 4);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
@@ -676,20 +677,27 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         tc_commit_elect(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
       issue_s(0);
       for (int i = 0; i < n_sub_u; ++i) {
         const int s = i % kKvStages;
+        KOCR_STAMP(i, 0);
         mbar_wait(&v_full[s], (i / kKvStages) & 1);
         if (i + 1 < n_sub_u) mbar_wait(&k_full[(i + 1) % kKvStages], ((i + 1) / kKvStages) & 1);  // off the critical path: before P arrives
+        KOCR_STAMP(i, 3);
         mbar_wait(&p_full[t], i & 1);
+        KOCR_STAMP(i, 4);
         tc_fence_after();
         const uint32_t va = v_lo + s * (kKvTileBytes >> 4);
 #pragma unroll
         for (int ks = 0; ks < kSub / 16; ++ks)
           umma_ts_lo(d_o, d_s + ks * 8, va + ks * (512 >> 4), hi32, idesc_o, (i > 0 || ks != 0));
         tc_commit_elect(&v_empty[s]);
+        KOCR_STAMP(i, 1);
         if (i + 1 < n_sub_u) issue_s(i + 1);
         else tc_commit_elect(&o_last[t]);
+        KOCR_STAMP(i, 2);
       }
     }
   } else {
@@ -714,13 +722,16 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int pp_mine = 1 + t * 4 + qtr, pp_next = 1 + ((t + 1) % kTiles) * 4 + qtr;
     if (kPP3 && t == kTiles - 1) named_bar_arrive(pp_next, 64);  // tile 0 goes first
     for (int i = 0; i < n_sub; ++i) {
+      KOCR_STAMP(i, 0);
       mbar_wait(&s_full[t], i & 1);  // S_t(i) complete; it was issued behind P_t(i-1).V, which is therefore complete as well
       tc_fence_after();
       uint32_t sr[kSub];
       tmem_ld_x32(t_s, sr);
       tmem_ld_x32(t_s + 32, sr + 32);
       tmem_ld_x16(t_s + 64, sr + 64);
+      KOCR_STAMP(i, 1);
       tc_wait_ld();
+      KOCR_STAMP(i, 2);
       const int valid = w.kv_len - i * kSub;
       if (valid < kSub) {
 #pragma unroll
@@ -753,6 +764,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         m_ref = mx;
       }
       float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      KOCR_STAMP(i, 3);
+      KOCR_STAMP(i, 4);
       if (kPP3) asm volatile("bar.sync %1, 64;" : "+f"(neg_m) : "r"(pp_mine) : "memory");
       const uint64_t neg_m2 = pack_f32x2(neg_m, neg_m);
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
@@ -787,6 +800,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         sum = (a0 + a1) + (b0 + b1);
       }
       l = l * alpha + sum;
+      KOCR_STAMP(i, 5);
       if (!KOCR_A3_EARLYST) {
         tmem_st_x16(t_s, pk);
         tmem_st_x16(t_s + 16, pk + 16);
@@ -800,9 +814,13 @@ attention3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         for (int c = 0; c < kHd; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
         tmem_st_cols<kHd>(t_o, o);
       }
+      KOCR_STAMP(i, 6);
+      KOCR_STAMP(i, 7);
       tc_wait_st();
+      KOCR_STAMP(i, 8);
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      KOCR_STAMP(i, 9);
     }
     mbar_wait(&o_last[t], 0);
     tc_fence_after();

@@ -19,29 +19,29 @@ for _ in range(3):
     gu.op_attention(qkv, cu, H)
 torch.cuda.synchronize()
 lib = C.CDLL(_lib.LIB_PATH)
-W, S, P = 12, 96, 12
+W, S, P = 16, 96, 12
 buf = np.zeros((W, S, P), dtype=np.int64)
 rc = lib.kocr_debug_attn_trace(C.c_void_p(buf.ctypes.data), C.c_int64(buf.nbytes))
 assert rc == 0, rc
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/attn_trace.npy", buf)
 lo, hi = 20, 70  # steady state
-names_s = ["wait s_full", "LDTM+wait::ld", "mask+row max", "token wait (bar.sync)", "exponents+sum", "STTM issue", "o_done wait", "rescale+wait::st", "fence+arrive", "loop back"]
+names_s = ["wait s_full (+LDTM issue in the three-tile kernel)", "LDTM+wait::ld", "mask+row max", "token wait (bar.sync)", "exponents+sum", "STTM issue", "o_done wait", "rescale+wait::st", "fence+arrive", "loop back"]
 print("softmax warps: mean cycles per phase over sub-steps %d..%d" % (lo, hi))
-for w in range(4, 12):
+for w in range(4, 16):
     t = buf[w]
     d = [np.mean(t[lo:hi, k + 1] - t[lo:hi, k]) for k in range(9)] + [np.mean(t[lo + 1:hi + 1, 0] - t[lo:hi, 9])]
     per = np.mean(t[lo + 1:hi + 1, 0] - t[lo:hi, 0])
     print(f"warp {w:2d} (tile {(w - 4) // 4}): period {per:7.1f} | " + " | ".join(f"{n} {x:6.1f}" for n, x in zip(names_s, d)))
 print("MMA warps: mean cycles")
-for w in (1, 2):
+for w in (1, 2, 3):
     t = buf[w]
     per = np.mean(t[lo + 1:hi + 1, 0] - t[lo:hi, 0])
     print(f"warp {w}: period {per:7.1f} | wait v_full {np.mean(t[lo:hi,3]-t[lo:hi,0]):6.1f} | wait p_full {np.mean(t[lo:hi,4]-t[lo:hi,3]):6.1f} | "
           f"issue P.V {np.mean(t[lo:hi,1]-t[lo:hi,4]):6.1f} | wait k_full + issue S {np.mean(t[lo:hi,2]-t[lo:hi,1]):6.1f}")
 # merged timeline of sub-steps 30..33, warps 4 and 8 (same lane quarter) + MMA warps
 ev = []
-for w, pts in ((4, range(10)), (8, range(10)), (1, (0, 3, 4, 1, 2)), (2, (0, 3, 4, 1, 2))):
+for w, pts in ((5, range(10)), (9, range(10)), (13, range(10)), (1, (0, 3, 4, 1, 2)), (2, (0, 3, 4, 1, 2)), (3, (0, 3, 4, 1, 2))):
     for i in range(30, 34):
         for k in pts:
             ev.append((int(buf[w, i, k]), w, i, k))
