@@ -60,7 +60,7 @@ def run_mine():
 
 ms = timed(run_mine)
 mine_v = mine.view(S, H, HD)
-line(f"this repo: attention_kernel via kocr_op_attention ({os.path.basename(_lib.LIB_PATH)})", ms, None, None)
+line(f"this repo: attention kernels via kocr_op_attention ({os.path.basename(_lib.LIB_PATH)})", ms, None, None)
 del qkv
 
 cu_t = torch.tensor(cu, dtype=torch.int32, device="cuda")
