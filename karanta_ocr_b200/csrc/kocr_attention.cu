@@ -7,7 +7,16 @@
 // Input is the tower's packed QKV buffer [S, heads*240] with, per head, 80 q | 80 k | 80 v columns; q is already
 // rotated and multiplied by head_dim^-0.5 * log2(e) (fused QKV GEMM epilogue), so scores are in the log2 domain.
 //
-// CTA = one 256-row query block of one sequence and one head; 384 threads:
+// Two kernels share the operand layouts, the online softmax and the MMA forms below.
+//
+// attention3_kernel (full attention, the one the tower launches): CTA = one 384-row query block (three 128-row tiles) of one
+// sequence and one head, 512 threads: warp 0 TMA, warps 1-3 one MMA issuer per tile, warps 4-15 softmax (three per TMEM lane
+// quarter = three per scheduler). Scores are SINGLE-buffered per tile (TMEM: S_t 80 columns with P written over the first 40,
+// O_t 80 columns, 3 x 160 = 480): S_t(i+1) is issued right behind P_t(i).V. Tiles without a valid row (a sequence's last
+// block) are skipped. See the comment at the kernel.
+//
+// attention_kernel<kWin> (windowed layers of Qwen2.5-VL; <false> is the two-tile full-attention kernel that attention3 replaced,
+// kept for A/B runs): CTA = one 256-row query block of one sequence and one head; 384 threads:
 //   warp 0      TMA producer: Q once, then a ring of K tiles and a ring of V tiles (80 keys each = one score sub-step)
 //   warps 1,2   MMA issuers (one per query tile): S_t = Q_t K^T (SS) and O_t += P_t V (P from TMEM, V MN-major)
 //   warps 4-7   softmax of query tile 0 (rows 0..127), one row per thread
